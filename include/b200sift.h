@@ -1,0 +1,221 @@
+/*
+ * b200sift.h -- C ABI of the B200-native (sm_100a) SIFT detect / describe /
+ * match hot path.
+ *
+ * The reference (sapt36/VFX_Image_Stitching) has no FFI layer: the boundary
+ * of its hot path is the Python module sift_impl (function-level API,
+ * sift_impl.py:15-526) plus compute_shift_sift's matcher loop
+ * (image_stitching_sift.py:52-83).  This header is what a ctypes shim with
+ * those function names binds (see INTEGRATION.md and
+ * vfx_image_stitching_b200/sift_impl.py); every entry point cites the
+ * reference lines it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA types in signatures
+ *     (a stream is passed as void* = cudaStream_t);
+ *   - every function returns 0 on success, a negative B200SIFT_E* code on
+ *     failure; b200sift_last_error() returns a thread-local message;
+ *   - "host" pointers may be pageable or pinned; functions with an
+ *     `on_device` flag also accept device pointers of the context's GPU;
+ *   - one context per (process, GPU); calls on one context are not
+ *     thread-safe and are synchronous from the caller's point of view;
+ *   - there is no CPU fallback: without a usable sm_100 device
+ *     b200sift_create fails.
+ */
+#ifndef B200SIFT_H
+#define B200SIFT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(B200SIFT_BUILD)
+#define B200SIFT_API __attribute__((visibility("default")))
+#else
+#define B200SIFT_API
+#endif
+
+#define B200SIFT_OK 0
+#define B200SIFT_EARG (-1)      /* bad argument */
+#define B200SIFT_ECUDA (-2)     /* CUDA runtime / driver error */
+#define B200SIFT_ECAPACITY (-3) /* fixed-capacity device buffer overflowed */
+#define B200SIFT_ESTATE (-4)    /* call order violated (e.g. no detect before match_images) */
+
+typedef struct b200sift_ctx b200sift_ctx;
+
+/* The cv2.KeyPoint fields the reference reads and writes (sift_impl.py:206-210,
+ * 290-291, 339-341); class_id is always -1 and is not carried. */
+typedef struct {
+    float x, y;     /* kp.pt */
+    float size;     /* kp.size */
+    float angle;    /* kp.angle, degrees in [0,360) */
+    float response; /* kp.response */
+    int32_t octave; /* kp.octave, packed: byte0 octave, byte1 layer, bits16+ sub-layer offset */
+} b200sift_keypoint;
+
+/* Keyword arguments / defaults of the reference, as one POD
+ * (sift_impl.py:15,117,170,247,361-362). */
+typedef struct {
+    double sigma;               /* 1.6  */
+    int32_t num_intervals;      /* 3    */
+    double assumed_blur;        /* 0.5  */
+    int32_t image_border_width; /* 5    */
+    double contrast_threshold;  /* 0.04 */
+    double eigen_ratio;         /* 10   */
+    int32_t max_iter;           /* 5    */
+    double radius_factor;       /* 3    */
+    int32_t ori_bins;           /* 36   */
+    double peak_ratio;          /* 0.8  */
+    double scale_factor;        /* 1.5  */
+    int32_t window_width;       /* 4   (fixed by the kernels) */
+    int32_t desc_bins;          /* 8   (fixed by the kernels) */
+    double scale_multiplier;    /* 3    */
+    double descriptor_max_value;/* 0.2  */
+} b200sift_params;
+
+/* image element types accepted by detect_describe */
+#define B200SIFT_U8 0
+#define B200SIFT_F32 1
+
+B200SIFT_API void b200sift_default_params(b200sift_params *p);
+B200SIFT_API const char *b200sift_last_error(void);
+/* version / build info, e.g. "b200sift 0.1 sm_100a" */
+B200SIFT_API const char *b200sift_version(void);
+
+B200SIFT_API int b200sift_create(int device, b200sift_ctx **ctx);
+B200SIFT_API void b200sift_destroy(b200sift_ctx *ctx);
+/* Run all work of this context on `cuda_stream` (a cudaStream_t; NULL = the
+ * context's own stream).  Lets a torch caller order work on its stream. */
+B200SIFT_API int b200sift_set_stream(b200sift_ctx *ctx, void *cuda_stream);
+/* Device time in ms of the kernels of the last detect_describe / match call
+ * (CUDA events on the context stream; host<->device copies excluded). */
+B200SIFT_API int b200sift_last_kernel_ms(b200sift_ctx *ctx, float *ms);
+/* Number of kernel launches issued by this context since creation. */
+B200SIFT_API int b200sift_launch_count(b200sift_ctx *ctx, long long *n);
+
+/* ---------------------------------------------------------------------
+ * Fused path: compute_keypoints_and_descriptors (sift_impl.py:15-39) for a
+ * batch of n_images images of identical shape (h rows, w cols, `channels`
+ * 1 or 3 = BGR, dtype u8 or f32 (f32 only with channels == 1)).
+ * images[i] points at image i (row stride in bytes).  Results stay on the
+ * device; n_keypoints[i] receives the keypoint count of image i.
+ * ------------------------------------------------------------------- */
+B200SIFT_API int b200sift_detect_describe(b200sift_ctx *ctx, const b200sift_params *params, int n_images,
+                             const void *const *images, int h, int w, int channels, int dtype,
+                             size_t row_stride, int on_device, int32_t *n_keypoints);
+
+/* Copy the results of image `image` of the last detect_describe to the host.
+ * Any of kps / desc_f32 / desc_u8 may be NULL.  Keypoints are in the order of
+ * remove_duplicate_keypoints (sift_impl.py:299-327) and already converted to
+ * input-image coordinates (:333-343); desc_* are (n,128) row-major
+ * (:361-526; integer valued 0..255). */
+B200SIFT_API int b200sift_get_keypoints(b200sift_ctx *ctx, int image, b200sift_keypoint *kps, float *desc_f32,
+                           uint8_t *desc_u8);
+
+/* Stage counters of the last detect_describe for image `image`:
+ * candidates that passed is_pixel_an_extremum (:143-163), candidates that
+ * survived localize_extremum_via_quadratic_fit (:169-211), oriented keypoints
+ * before de-duplication (:246-293). */
+B200SIFT_API int b200sift_get_stats(b200sift_ctx *ctx, int image, int32_t *n_candidates, int32_t *n_localized,
+                       int32_t *n_oriented);
+
+/* Device-resident views of image `image`'s results (valid until the next
+ * detect_describe on this context): used by the multi-GPU descriptor
+ * all-gather and by callers that keep everything on the GPU. */
+B200SIFT_API int b200sift_device_results(b200sift_ctx *ctx, int image, const uint8_t **d_desc_u8,
+                            const b200sift_keypoint **d_kps, int32_t *n);
+
+/* ---------------------------------------------------------------------
+ * Matcher: the A->B nearest-neighbour loop of compute_shift_sift
+ * (image_stitching_sift.py:63-73) on uint8 descriptors, exact integer
+ * arithmetic, lowest j wins ties.  best_idx[i] = argmin_j |A_i-B_j|^2
+ * (-1 if nB == 0), best_d2 / second_d2 = smallest and second smallest
+ * squared distance (INT32_MAX if absent).  second_d2 may be NULL.
+ * ------------------------------------------------------------------- */
+B200SIFT_API int b200sift_match(b200sift_ctx *ctx, const uint8_t *A, int nA, const uint8_t *B, int nB,
+                   int on_device, int32_t *best_idx, int32_t *best_d2, int32_t *second_d2);
+
+/* compute_shift_sift's match list (image_stitching_sift.py:63-79) between two
+ * images of the last detect_describe: accepted iff best_d2 < desc_thresh.
+ * ia/ib (capacity = keypoints of imgA) receive the A / B keypoint indices in
+ * A order, xyxy (n x 4) the (xA,yA,xB,yB) coordinates; *n_matches the count. */
+B200SIFT_API int b200sift_match_images(b200sift_ctx *ctx, int imgA, int imgB, int desc_thresh, int32_t *ia,
+                          int32_t *ib, float *xyxy, int32_t *n_matches);
+
+/* ransac() translation vote (image_stitching_sift.py:86-111) on the device:
+ * matches n x 4 float (xA,yA,xB,yB); returns the winning index in *best
+ * (first maximum; -1 when n == 0) and its (dx,dy) in move[2]. */
+B200SIFT_API int b200sift_ransac(b200sift_ctx *ctx, const float *matches, int n, double dist_sq_thresh,
+                    double *move, int32_t *best);
+
+/* ---------------------------------------------------------------------
+ * Stage API (what sift_visualizeUI.py:104-115 calls one by one).  Host
+ * arrays in, host arrays out; the work runs on the GPU.
+ * ------------------------------------------------------------------- */
+
+/* cv2.GaussianBlur(src,(0,0),sigma) on float32 (sift_impl.py:56,91): h x w,
+ * dense rows.  on_device: src/dst are device pointers (used by the roofline
+ * bench; no copies, asynchronous until b200sift_sync). */
+B200SIFT_API int b200sift_gaussian_blur(b200sift_ctx *ctx, const float *src, int h, int w, double sigma,
+                           float *dst, int on_device);
+B200SIFT_API int b200sift_sync(b200sift_ctx *ctx);
+
+/* generate_base_image (sift_impl.py:45-56): image h x w float32 -> out 2h x 2w. */
+B200SIFT_API int b200sift_base_image(b200sift_ctx *ctx, const float *image, int h, int w, double sigma,
+                        double assumed_blur, float *out);
+
+/* generate_gaussian_images (sift_impl.py:82-97): base h x w; sigmas[n_layers]
+ * (index 0 unused, as in the reference); out_layers[o*n_layers+l] receives the
+ * dense (h>>o) x (w>>o) layer. */
+B200SIFT_API int b200sift_gaussian_pyramid(b200sift_ctx *ctx, const float *base, int h, int w, int n_octaves,
+                              const double *sigmas, int n_layers, float *const *out_layers);
+
+/* generate_DoG_images (sift_impl.py:100-111) for one octave-layer pair list:
+ * layers as produced above; out_dogs[o*(n_layers-1)+l] = layer[l+1]-layer[l]. */
+B200SIFT_API int b200sift_dog_pyramid(b200sift_ctx *ctx, const float *const *layers, int h, int w, int n_octaves,
+                         int n_layers, float *const *out_dogs);
+
+/* find_scale_space_extrema (sift_impl.py:117-140) on a caller-supplied
+ * Gaussian pyramid (DoG = float32 difference of adjacent layers, as :109).
+ * Keypoints come back in the reference's scan order, in base-image
+ * coordinates, not de-duplicated.  *n receives the count (<= capacity). */
+B200SIFT_API int b200sift_find_extrema(b200sift_ctx *ctx, const b200sift_params *params,
+                          const float *const *layers, int h, int w, int n_octaves, int n_layers,
+                          b200sift_keypoint *kps, int capacity, int32_t *n);
+
+/* remove_duplicate_keypoints (sift_impl.py:314-327): sort by compare_keypoints
+ * (:299-311) and drop repeats; in place, *n_out receives the new count. */
+B200SIFT_API int b200sift_remove_duplicates(b200sift_ctx *ctx, b200sift_keypoint *kps, int n, int32_t *n_out);
+
+/* generate_descriptors (sift_impl.py:361-526) for keypoints already converted
+ * to input-image size, on a caller-supplied Gaussian pyramid. */
+B200SIFT_API int b200sift_descriptors(b200sift_ctx *ctx, const b200sift_params *params,
+                         const b200sift_keypoint *kps, int n, const float *const *layers, int h,
+                         int w, int n_octaves, int n_layers, float *desc_f32);
+
+/* Candidate stage alone (is_pixel_an_extremum, sift_impl.py:143-163): returns
+ * (octave, layer, y, x) int32 quadruples in scan order. */
+B200SIFT_API int b200sift_extrema_candidates(b200sift_ctx *ctx, const b200sift_params *params,
+                                const float *const *layers, int h, int w, int n_octaves,
+                                int n_layers, int32_t *cand, int capacity, int32_t *n);
+
+/* cylindrical_projection (image_stitching_sift.py:117-136), uint8 h x w x ch. */
+B200SIFT_API int b200sift_cylindrical_projection(b200sift_ctx *ctx, const uint8_t *src, int h, int w, int ch,
+                                    double focal, uint8_t *dst);
+
+/* Measurement hook for the roofline line of bench.py: runs `iters` launches of
+ * the Gaussian blur kernel for `sigma` on an internal n_img x h x w float32
+ * batch (pitch = w rounded up to 8) that is already resident in HBM, and
+ * returns the mean device time per launch in ms (CUDA events on the context
+ * stream).  flush_l2 != 0 writes a 256 MiB scratch buffer before every timed
+ * launch.  Algorithmic traffic of one launch: 8 * n_img * h * w bytes. */
+B200SIFT_API int b200sift_bench_blur(b200sift_ctx *ctx, int n_img, int h, int w, double sigma, int iters,
+                                     int flush_l2, float *ms_per_launch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SIFT_H */

@@ -53,14 +53,16 @@ typedef struct {
 /* ------------------------------------------------------------------ */
 
 /* cv2.cvtColor(COLOR_BGR2GRAY) on uint8 (sift_impl.py:27-28): fixed point,
- * (B*1868 + G*9617 + R*4899 + 8192) >> 14. */
+ * (B*3735 + G*19235 + R*9798 + 16384) >> 15 (OpenCV 4.13 uses 15-bit
+ * coefficients; checked against cv2 on 2M random pixels: 0 mismatches; the
+ * 14-bit set 1868/9617/4899 mismatches 0.26 %). */
 void orc_bgr2gray(const uint8_t *bgr, int h, int w, int stride, uint8_t *gray)
 {
     for (int y = 0; y < h; ++y) {
         const uint8_t *p = bgr + (size_t)y * stride;
         for (int x = 0; x < w; ++x)
             gray[(size_t)y * w + x] =
-                (uint8_t)((p[3 * x] * 1868 + p[3 * x + 1] * 9617 + p[3 * x + 2] * 4899 + 8192) >> 14);
+                (uint8_t)((p[3 * x] * 3735 + p[3 * x + 1] * 19235 + p[3 * x + 2] * 9798 + 16384) >> 15);
     }
 }
 

@@ -1,0 +1,88 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every
+symbol include/b200sift.h declares; the ctypes layer binds all of them; the product path fails
+loudly (no CPU fallback) when there is no GPU."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, _has_gpu
+
+
+def _declared():
+    src = open(os.path.join(ROOT, 'include', 'b200sift.h')).read()
+    return sorted(set(re.findall(r'B200SIFT_API[^;(]*?\b(b200sift_\w+)\s*\(', src)))
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    from vfx_image_stitching_b200 import build
+    path = build.build()
+    lib = ctypes.CDLL(path)
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f'{n} declared in include/b200sift.h but not exported'
+
+
+def test_ctypes_prototypes_cover_header():
+    from vfx_image_stitching_b200 import _capi
+    assert sorted(_capi.PROTOTYPES) == _declared()
+    lib = _capi.load()
+    assert lib.b200sift_version().decode().startswith('b200sift')
+    p = _capi.default_params()
+    assert (p.sigma, p.num_intervals, p.assumed_blur, p.image_border_width) == (1.6, 3, 0.5, 5)
+    assert (p.contrast_threshold, p.eigen_ratio, p.max_iter) == (0.04, 10, 5)
+    assert (p.radius_factor, p.ori_bins, p.peak_ratio, p.scale_factor) == (3, 36, 0.8, 1.5)
+    assert (p.window_width, p.desc_bins, p.scale_multiplier, p.descriptor_max_value) == (4, 8, 3, 0.2)
+    assert _capi.KP_DTYPE.itemsize == 24
+
+
+def test_reference_signatures_are_preserved():
+    """Names, positional order and defaults of sift_impl.py / image_stitching_sift.py."""
+    import inspect
+    from vfx_image_stitching_b200 import sift_impl, image_stitching_sift
+
+    def sig(f):
+        return [(p.name, p.default if p.default is not inspect._empty else None)
+                for p in inspect.signature(f).parameters.values()]
+    assert sig(sift_impl.compute_keypoints_and_descriptors) == [
+        ('image', None), ('sigma', 1.6), ('num_intervals', 3), ('assumed_blur', 0.5), ('image_border_width', 5)]
+    assert sig(sift_impl.generate_base_image) == [('image', None), ('sigma', None), ('assumed_blur', None)]
+    assert sig(sift_impl.generate_gaussian_images) == [('image', None), ('num_octaves', None), ('gaussian_kernels', None)]
+    assert sig(sift_impl.find_scale_space_extrema) == [
+        ('gaussian_images', None), ('dog_images', None), ('num_intervals', None), ('sigma', None), ('border', None),
+        ('contrast_threshold', 0.04)]
+    assert sig(sift_impl.generate_descriptors) == [
+        ('keypoints', None), ('gaussian_images', None), ('window_width', 4), ('num_bins', 8),
+        ('scale_multiplier', 3), ('descriptor_max_value', 0.2)]
+    assert sig(image_stitching_sift.compute_shift_sift)[:4] == [
+        ('imgA', None), ('imgB', None), ('ransac_thr', 3), ('desc_thresh', 25000)]
+    assert sig(image_stitching_sift.ransac)[:2] == [('matches', None), ('dist_sq_thresh', 3)]
+    assert sift_impl.float_tolerance == 1e-7
+    for name in ('compute_number_of_octaves', 'generate_gaussian_kernels', 'generate_DoG_images',
+                 'is_pixel_an_extremum', 'compute_gradient_at_center_pixel', 'compute_hessian_at_center_pixel',
+                 'compare_keypoints', 'remove_duplicate_keypoints', 'convert_keypoints_to_input_image_size',
+                 'unpack_octave'):
+        assert callable(getattr(sift_impl, name))
+
+
+def test_host_side_parameter_arithmetic_matches_oracle(oracle):
+    from vfx_image_stitching_b200 import sift_impl
+    assert np.array_equal(sift_impl.generate_gaussian_kernels(1.6, 3), oracle.generate_gaussian_kernels(1.6, 3))
+    for shape in ((1024, 768), (1142, 856), (8192, 6144), (10, 14), (4, 4)):
+        assert sift_impl.compute_number_of_octaves(shape) == oracle.compute_number_of_octaves(shape)
+    k = sift_impl.array_to_keypoints(np.array([(3.5, 4.25, 2.0, 90.0, 0.1, 0x2FF)], sift_impl.KP_DTYPE))[0]
+    assert sift_impl.unpack_octave(k)[:2] == (-1, 2) and sift_impl.unpack_octave(k)[2] == 2.0
+    k.octave = 0x10301
+    sift_impl.convert_keypoints_to_input_image_size([k])
+    assert k.pt == (1.75, 2.125) and k.size == 1.0 and k.octave == 0x10300
+
+
+@pytest.mark.skipif(_has_gpu(), reason='checks the behaviour WITHOUT a GPU')
+def test_no_cpu_fallback_without_gpu():
+    from vfx_image_stitching_b200 import sift_impl
+    from vfx_image_stitching_b200._capi import B200SiftError
+    with pytest.raises(B200SiftError):
+        sift_impl.compute_keypoints_and_descriptors(np.zeros((32, 32), np.uint8))

@@ -1,0 +1,88 @@
+"""The N>1 plumbing (image-block sharding, all-gather of block-first descriptors, pair ownership)
+on CPU with gloo, world_size 2 and 3.  Compute is injected: here the oracle plays the kernels, so
+the test checks that every world size returns exactly the single-process result."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _oracle_ops():
+    from oracle import sift_oracle as so
+    from vfx_image_stitching_b200.panorama import Ops
+
+    def detect(images):
+        out = []
+        for im in images:
+            k, d = so.compute_keypoints_and_descriptors(im)
+            out.append((k, np.asarray(d, np.float32).reshape(-1, 128).astype(np.uint8)))
+        return out
+
+    def match(kA, dA, kB, dB, thresh):
+        idx, d1, _ = so.match_u8(dA, dB)
+        keep = (d1 < thresh) & (idx != -1)
+        ia = np.nonzero(keep)[0]
+        ib = idx[keep]
+        return np.stack([kA['x'][ia], kA['y'][ia], kB['x'][ib], kB['y'][ib]], 1).astype(np.float64) \
+            if len(ia) else np.zeros((0, 4))
+
+    return Ops(detect, match, lambda m, thr: so.ransac(m, thr)[0])
+
+
+def _images():
+    from vfx_image_stitching_b200.synthetic import panorama_set
+    return panorama_set(5, 96, 128, seed=7, shift=(-2, -40))
+
+
+def _worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import torch.distributed as dist
+    from vfx_image_stitching_b200.panorama import sharded_panorama_shifts
+    dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
+    try:
+        shifts, counts = sharded_panorama_shifts(_images(), _oracle_ops(), dist=dist, device='cpu')
+        q.put((rank, shifts, counts))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_ranges():
+    from vfx_image_stitching_b200.panorama import shard_range
+    assert [shard_range(18, r, 8)[1] - shard_range(18, r, 8)[0] for r in range(8)] == [3, 3, 2, 2, 2, 2, 2, 2]
+    for n, w in ((18, 1), (18, 4), (5, 8), (64, 8), (0, 2)):
+        blocks = [shard_range(n, r, w) for r in range(w)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
+
+
+@pytest.mark.parametrize('world', [2, 3])
+def test_sharded_equals_single_process(world):
+    import torch.multiprocessing as mp
+    from vfx_image_stitching_b200.panorama import sharded_panorama_shifts
+    ref_shifts, ref_counts = sharded_panorama_shifts(_images(), _oracle_ops())
+    assert len(ref_shifts) == 4 and sum(abs(abs(s[0]) - 40) < 1.0 and abs(abs(s[1]) - 2) < 1.0 for s in ref_shifts) >= 3
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, shifts, counts in got:
+        assert shifts == ref_shifts and counts == ref_counts, rank

@@ -1,0 +1,189 @@
+// Shared declarations of the b200sift CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/b200sift.h"
+
+namespace b200 {
+
+void set_error(const char *fmt, ...);
+
+#define B200_CUDA(call)                                                              \
+    do {                                                                             \
+        cudaError_t e__ = (call);                                                    \
+        if (e__ != cudaSuccess) {                                                    \
+            b200::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,             \
+                            cudaGetErrorString(e__));                                \
+            return B200SIFT_ECUDA;                                                   \
+        }                                                                            \
+    } while (0)
+
+#define B200_CHECK(expr)                 \
+    do {                                 \
+        int rc__ = (expr);               \
+        if (rc__ != 0) return rc__;      \
+    } while (0)
+
+#define B200_ARG(cond)                                                   \
+    do {                                                                 \
+        if (!(cond)) {                                                   \
+            b200::set_error("%s:%d bad argument: %s", __FILE__, __LINE__, #cond); \
+            return B200SIFT_EARG;                                        \
+        }                                                                \
+    } while (0)
+
+constexpr int kMaxOctaves = 24;
+constexpr int kMaxLayers = 10;  // num_intervals + 3 <= 10
+constexpr int kMaxBlurRadius = 64;
+
+// Gaussian pyramid of a batch of same-shape images, resident in HBM.
+// Layer-major inside an octave: [layer][image][row][pitch] float32, so that
+// one blur launch covers a whole layer of all images; pitch is the row
+// length rounded up to 8 floats (32 B sectors, float4-aligned rows).
+struct Pyramid {
+    int n_img = 0, n_oct = 0, n_layers = 0;
+    int h[kMaxOctaves], w[kMaxOctaves], pitch[kMaxOctaves];
+    size_t oct_off[kMaxOctaves];  // float offset of octave o
+    float *base = nullptr;        // device allocation
+    size_t floats = 0, capacity_floats = 0;
+    __host__ __device__ size_t img_stride(int o) const { return (size_t)h[o] * pitch[o]; }
+    __host__ __device__ float *layer(int o, int l, int img = 0) const {
+        return base + oct_off[o] + ((size_t)l * n_img + img) * img_stride(o);
+    }
+};
+
+// Device-side view handed to the detection kernels (no host pointers inside).
+struct PyrView {
+    int n_img, n_oct, n_layers;
+    int h[kMaxOctaves], w[kMaxOctaves], pitch[kMaxOctaves];
+    const float *oct[kMaxOctaves];  // base of octave o
+    __device__ __forceinline__ const float *layer(int o, int l, int img) const {
+        return oct[o] + ((size_t)l * n_img + img) * ((size_t)h[o] * pitch[o]);
+    }
+};
+
+// 3x3x3 extremum that passed is_pixel_an_extremum.
+struct Candidate {
+    uint32_t img_o_l;  // img << 16 | octave << 8 | layer
+    uint32_t yx;       // y << 16 | x
+};
+
+// Localized extremum (output of the quadratic fit), input of orientation.
+struct Localized {
+    float x, y, size, response;  // base-image coordinates (before the 0.5 conversion)
+    int32_t octave_packed;
+    uint32_t img_o_l;            // img << 16 | octave << 8 | final layer
+    uint64_t order;              // scan-order key of the originating candidate
+};
+
+// Oriented keypoint before sorting.
+struct RawKeypoint {
+    float x, y, size, angle, response;
+    int32_t octave_packed;
+    uint32_t img;
+    uint32_t pad;
+    uint64_t order;  // (candidate scan order << 6) | peak bin
+};
+
+struct DetectParams {
+    int num_intervals, border, max_iter, ori_bins;
+    float dog_thresh;       // floor(0.5*contrast/num_intervals*255)
+    float contrast_thr_f;   // (float)contrast_threshold
+    float eigen_ratio_f;
+    float sigma_f;
+    float radius_factor_f;
+    double scale_factor;
+    double peak_ratio;
+    double scale_multiplier_half;  // scale_multiplier*0.5
+    float descriptor_max_value_f;
+};
+
+}  // namespace b200
+
+struct b200sift_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    long long launches = 0;
+
+    b200::Pyramid pyr;
+    float *d_up = nullptr;  size_t up_cap = 0;     // upsampled (pre-blur) base, [img][2h][pitch0]
+    uint8_t *d_in = nullptr; size_t in_cap = 0;    // uploaded input images
+    float *d_dog = nullptr; size_t dog_cap = 0;    // materialised DoG (stage API only)
+
+    // sparse stage
+    b200::Candidate *d_cand = nullptr; int cand_cap = 0;
+    b200::Localized *d_loc = nullptr;  int loc_cap = 0;
+    b200::RawKeypoint *d_raw = nullptr; int raw_cap = 0;
+    uint8_t *d_raw_desc = nullptr;                 // [raw_cap][128]
+    uint32_t *d_sort_idx = nullptr; uint32_t *d_keep = nullptr; uint32_t *d_pos = nullptr;
+    void *d_cub_tmp = nullptr; size_t cub_tmp_cap = 0;
+    b200sift_keypoint *d_kps = nullptr;            // final, compact, image-major
+    uint8_t *d_desc = nullptr;                     // final [n][128]
+    int out_cap = 0;
+    // counters: [0]=n_cand [1]=n_loc [2]=n_raw [3]=n_out [4]=overflow flags ; then per image x4
+    int32_t *d_counters = nullptr; int32_t *h_counters = nullptr; int counters_len = 0;
+    std::vector<int> img_off;      // n_img+1 prefix of final keypoints per image
+    std::vector<int> stat_cand, stat_loc, stat_raw;
+    int n_img_last = 0;
+    bool have_results = false;
+
+    // matcher scratch
+    uint8_t *d_mA = nullptr, *d_mB = nullptr; size_t mA_cap = 0, mB_cap = 0;
+    int32_t *d_mout = nullptr; size_t mout_cap = 0;
+    int32_t *d_nrmB = nullptr; size_t nrmB_cap = 0;
+    void *d_misc = nullptr; size_t misc_cap = 0;
+};
+
+namespace b200 {
+
+template <typename T>
+int ensure(T **p, size_t *cap, size_t need)
+{
+    if (need <= *cap && *p) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    size_t n = need + need / 4 + 256;
+    cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+    if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu bytes) -> %s", n * sizeof(T), cudaGetErrorString(e));
+        *cap = 0;
+        return B200SIFT_ECUDA;
+    }
+    *cap = n;
+    return 0;
+}
+
+// pyramid.cu
+int pyramid_layout(b200sift_ctx *c, int n_img, int h0, int w0, int n_oct, int n_layers);
+int launch_gray_upsample(b200sift_ctx *c, const void *d_in, size_t img_stride_bytes, size_t row_stride,
+                         int n_img, int h, int w, int channels, int dtype, float *d_out, int out_pitch);
+int launch_blur(b200sift_ctx *c, const float *src, float *dst, int n_img, int h, int w, int pitch,
+                size_t img_stride, double sigma, float *dst2, int h2, int w2, int pitch2,
+                size_t img_stride2);
+int build_octaves(b200sift_ctx *c, const double *sigmas);
+int base_blur(b200sift_ctx *c, const float *d_up, double sigma_diff);
+int launch_dog(b200sift_ctx *c, const float *a, const float *b, float *out, size_t n);
+// detect.cu
+PyrView make_view(const Pyramid &p);
+DetectParams make_detect_params(const b200sift_params &p);
+int run_detect(b200sift_ctx *c, const b200sift_params &p, int want_scan_order);
+int run_describe(b200sift_ctx *c, const b200sift_params &p, const RawKeypoint *d_raw, int n, int converted,
+                 uint8_t *d_out);
+int run_sort_gather(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int dedupe, int convert, int with_desc);
+int ensure_sparse_for(b200sift_ctx *c, int n_img, int n_raw);
+int launch_ransac(b200sift_ctx *c, const float *d_matches, int n, double thr, double *move, int32_t *best);
+int launch_cyl(b200sift_ctx *c, const uint8_t *d_src, int h, int w, int ch, double f, uint8_t *d_dst);
+// match.cu
+int run_match(b200sift_ctx *c, const uint8_t *dA, int nA, const uint8_t *dB, int nB, int32_t *d_best_idx,
+              int32_t *d_best_d2, int32_t *d_second_d2);
+int run_accept(b200sift_ctx *c, const int32_t *d_idx, const int32_t *d_d2, int nA, int thresh,
+               const b200sift_keypoint *kA, const b200sift_keypoint *kB, int32_t *d_ia, int32_t *d_ib,
+               float *d_xyxy, int32_t *d_count);
+
+}  // namespace b200

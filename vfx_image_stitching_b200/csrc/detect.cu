@@ -1,0 +1,923 @@
+// Sparse stage of the SIFT path: fused DoG + 3x3x3 extrema scan with
+// warp-ballot compaction, quadratic-fit refinement, warp-per-keypoint
+// orientation histograms and 4x4x8 descriptors, ordering + de-duplication.
+//
+// Replaces (all in /root/reference/sift_impl.py): :100-111 (DoG, fused, never
+// materialised), :117-163 find_scale_space_extrema / is_pixel_an_extremum,
+// :169-240 localize_extremum_via_quadratic_fit + gradient / Hessian,
+// :246-293 compute_keypoints_with_orientations, :299-327 compare_keypoints /
+// remove_duplicate_keypoints, :333-343 convert_keypoints_to_input_image_size,
+// :349-526 unpack_octave / generate_descriptors.
+//
+// This file is compiled with --fmad=false: numpy rounds every float32
+// operation once, so must we (the float64 solve then agrees bit for bit with
+// a no-FMA CPU evaluation of the same expressions).
+#include <cub/device/device_merge_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <math.h>
+#include "common.cuh"
+
+namespace b200 {
+
+// counters layout
+enum { CNT_CAND = 0, CNT_LOC = 1, CNT_RAW = 2, CNT_OUT = 3, CNT_HDR = 8, CNT_PER_IMG = 4 };
+
+PyrView make_view(const Pyramid &p)
+{
+    PyrView v;
+    v.n_img = p.n_img;
+    v.n_oct = p.n_oct;
+    v.n_layers = p.n_layers;
+    for (int o = 0; o < p.n_oct; ++o) {
+        v.h[o] = p.h[o];
+        v.w[o] = p.w[o];
+        v.pitch[o] = p.pitch[o];
+        v.oct[o] = p.base + p.oct_off[o];
+    }
+    return v;
+}
+
+DetectParams make_detect_params(const b200sift_params &p)
+{
+    DetectParams d;
+    d.num_intervals = p.num_intervals;
+    d.border = p.image_border_width;
+    d.max_iter = p.max_iter;
+    d.ori_bins = p.ori_bins;
+    d.dog_thresh = (float)floor(0.5 * p.contrast_threshold / p.num_intervals * 255);  // sift_impl.py:122
+    d.contrast_thr_f = (float)p.contrast_threshold;
+    d.eigen_ratio_f = (float)p.eigen_ratio;
+    d.sigma_f = (float)p.sigma;
+    d.radius_factor_f = (float)p.radius_factor;
+    d.scale_factor = p.scale_factor;
+    d.peak_ratio = p.peak_ratio;
+    d.scale_multiplier_half = p.scale_multiplier * 0.5;
+    d.descriptor_max_value_f = (float)p.descriptor_max_value;
+    return d;
+}
+
+// ---------------------------------------------------------------------------
+// fused DoG + extrema scan (sift_impl.py:109, :124-132, :143-163)
+// One CTA = 32x16 scan pixels of one image at one octave.  The DoG stack of
+// the tile (+1 halo) is formed in shared memory from the Gaussian layers
+// (float32 subtraction, never written to HBM: 24 B read per pixel for six
+// layers); each thread tests its pixels in the num_intervals middle layers;
+// hits are compacted with a warp ballot and one atomic per warp.
+// ---------------------------------------------------------------------------
+constexpr int kExTW = 32, kExTH = 16;
+
+__global__ void __launch_bounds__(256)
+extrema_kernel(PyrView v, int o, int border, int num_intervals, float thresh, Candidate *__restrict__ cand,
+               int cand_cap, int32_t *__restrict__ counters)
+{
+    extern __shared__ float dog_s[];  // [n_dog][(TH+2)*(TW+2)]
+    constexpr int SW = kExTW + 2, SH = kExTH + 2, SN = SW * SH;
+    const int img = blockIdx.z;
+    const int h = v.h[o], w = v.w[o], pitch = v.pitch[o];
+    const int n_dog = v.n_layers - 1;
+    const int x0 = border + blockIdx.x * kExTW, y0 = border + blockIdx.y * kExTH;
+    const size_t lstride = (size_t)v.n_img * h * pitch;  // layer stride
+    const float *g0 = v.layer(o, 0, img);
+    for (int i = threadIdx.x; i < SN; i += 256) {
+        const int yy = i / SW, xx = i - yy * SW;
+        const int y = min(max(y0 - 1 + yy, 0), h - 1), x = min(max(x0 - 1 + xx, 0), w - 1);
+        const float *p = g0 + (size_t)y * pitch + x;
+        float prev = *p;
+        for (int l = 0; l < n_dog; ++l) {
+            p += lstride;
+            const float cur = *p;
+            dog_s[l * SN + i] = __fsub_rn(cur, prev);
+            prev = cur;
+        }
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const unsigned lane = tx;
+    for (int k = 0; k < kExTH / 8; ++k) {
+        const int yl = ty + 8 * k;
+        const int y = y0 + yl, x = x0 + tx;
+        const bool inside = (y < h - border) && (x < w - border);
+        const int ctr = (yl + 1) * SW + tx + 1;
+        for (int l = 1; l <= num_intervals; ++l) {
+            bool ext = false;
+            if (inside) {
+                const float *c = dog_s + l * SN + ctr;
+                const float val = *c;
+                if (fabsf(val) > thresh) {
+                    ext = true;
+                    if (val > 0.f) {
+#pragma unroll
+                        for (int dl = -1; dl <= 1; ++dl)
+#pragma unroll
+                            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                                for (int dx = -1; dx <= 1; ++dx) ext = ext && (val >= c[dl * SN + dy * SW + dx]);
+                    } else {
+#pragma unroll
+                        for (int dl = -1; dl <= 1; ++dl)
+#pragma unroll
+                            for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+                                for (int dx = -1; dx <= 1; ++dx) ext = ext && (val <= c[dl * SN + dy * SW + dx]);
+                    }
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ext);
+            if (m) {
+                int base = 0;
+                if (lane == (unsigned)(__ffs(m) - 1)) {
+                    base = atomicAdd(&counters[CNT_CAND], __popc(m));
+                    atomicAdd(&counters[CNT_HDR + img * CNT_PER_IMG + 0], __popc(m));
+                }
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                if (ext) {
+                    const int idx = base + __popc(m & ((1u << lane) - 1u));
+                    if (idx < cand_cap) {
+                        Candidate cd;
+                        cd.img_o_l = ((uint32_t)img << 16) | ((uint32_t)o << 8) | (uint32_t)l;
+                        cd.yx = ((uint32_t)y << 16) | (uint32_t)x;
+                        cand[idx] = cd;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// quadratic-fit refinement (sift_impl.py:169-240), one thread per candidate
+// ---------------------------------------------------------------------------
+
+// x = pinv(H) g for symmetric 3x3 H in float64 (cyclic Jacobi): the
+// minimum-norm least-squares solution np.linalg.lstsq(hess, grad, rcond=None)
+// returns (LAPACK gelsd, cut-off eps*3*|lambda|max).
+__device__ void sym3_pinv_solve(const double H[3][3], const double g[3], double x[3])
+{
+    double a[3][3], v[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            a[i][j] = H[i][j];
+            v[i][j] = (i == j) ? 1.0 : 0.0;
+        }
+    for (int sweep = 0; sweep < 60; ++sweep) {
+        const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
+        if (off == 0.0) break;
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+#pragma unroll
+            for (int q = p + 1; q < 3; ++q) {
+                if (a[p][q] == 0.0) continue;
+                const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = c * akp - s * akq;
+                    a[k][q] = s * akp + c * akq;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = c * apk - s * aqk;
+                    a[q][k] = s * apk + c * aqk;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const double vkp = v[k][p], vkq = v[k][q];
+                    v[k][p] = c * vkp - s * vkq;
+                    v[k][q] = s * vkp + c * vkq;
+                }
+            }
+    }
+    const double lmax = fmax(fabs(a[0][0]), fmax(fabs(a[1][1]), fabs(a[2][2])));
+    const double cut = 2.220446049250313e-16 * 3.0 * lmax;
+    x[0] = x[1] = x[2] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double lam = a[i][i];
+        if (!(fabs(lam) > cut)) continue;
+        const double proj = (v[0][i] * g[0] + v[1][i] * g[1] + v[2][i] * g[2]) / lam;
+        x[0] += proj * v[0][i];
+        x[1] += proj * v[1][i];
+        x[2] += proj * v[2][i];
+    }
+}
+
+__global__ void __launch_bounds__(128)
+refine_kernel(PyrView v, DetectParams dp, const Candidate *__restrict__ cand, int cand_cap,
+              Localized *__restrict__ loc, int loc_cap, int32_t *__restrict__ counters)
+{
+    const int n = min(counters[CNT_CAND], cand_cap);
+    for (int ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += gridDim.x * blockDim.x) {
+        const Candidate cd = cand[ci];
+        const int img = cd.img_o_l >> 16, o = (cd.img_o_l >> 8) & 255;
+        int layer = cd.img_o_l & 255;
+        int y = cd.yx >> 16, x = cd.yx & 0xffff;
+        const uint64_t order = ((((uint64_t)o << 4) | (uint64_t)layer) << 30) | ((uint64_t)y << 15) | (uint64_t)x;
+        const int h = v.h[o], w = v.w[o], pitch = v.pitch[o];
+        const size_t lstride = (size_t)v.n_img * h * pitch;
+        const float *g0 = v.layer(o, 0, img);
+        float cube[3][3][3], grad[3], hess[3][3], upd[3];
+        bool alive = true;
+        for (int it = 0; it < dp.max_iter; ++it) {
+            // cube[s][j][i] = DoG(layer-1+s)(y-1+j, x-1+i) / 255  (float32)
+            const float *p = g0 + (size_t)(layer - 1) * lstride + (size_t)(y - 1) * pitch + (x - 1);
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const float *q = p + j * pitch + i;
+                    const float a0 = q[0], a1 = q[lstride], a2 = q[2 * lstride], a3 = q[3 * lstride];
+                    cube[0][j][i] = __fdiv_rn(__fsub_rn(a1, a0), 255.f);
+                    cube[1][j][i] = __fdiv_rn(__fsub_rn(a2, a1), 255.f);
+                    cube[2][j][i] = __fdiv_rn(__fsub_rn(a3, a2), 255.f);
+                }
+            grad[0] = 0.5f * (cube[1][1][2] - cube[1][1][0]);
+            grad[1] = 0.5f * (cube[1][2][1] - cube[1][0][1]);
+            grad[2] = 0.5f * (cube[2][1][1] - cube[0][1][1]);
+            const float c = cube[1][1][1];
+            const float dxx = cube[1][1][2] - 2 * c + cube[1][1][0];
+            const float dyy = cube[1][2][1] - 2 * c + cube[1][0][1];
+            const float dss = cube[2][1][1] - 2 * c + cube[0][1][1];
+            const float dxy = 0.25f * (cube[1][2][2] - cube[1][2][0] - cube[1][0][2] + cube[1][0][0]);
+            const float dxs = 0.25f * (cube[2][1][2] - cube[2][1][0] - cube[0][1][2] + cube[0][1][0]);
+            const float dys = 0.25f * (cube[2][2][1] - cube[2][0][1] - cube[0][2][1] + cube[0][0][1]);
+            hess[0][0] = dxx; hess[0][1] = dxy; hess[0][2] = dxs;
+            hess[1][0] = dxy; hess[1][1] = dyy; hess[1][2] = dys;
+            hess[2][0] = dxs; hess[2][1] = dys; hess[2][2] = dss;
+            double Hd[3][3], gd[3], xd[3];
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+                gd[i] = grad[i];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) Hd[i][j] = hess[i][j];
+            }
+            sym3_pinv_solve(Hd, gd, xd);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) upd[i] = -(float)xd[i];
+            if (fabsf(upd[0]) < 0.5f && fabsf(upd[1]) < 0.5f && fabsf(upd[2]) < 0.5f) break;
+            x += (int)rintf(upd[0]);
+            y += (int)rintf(upd[1]);
+            layer += (int)rintf(upd[2]);
+            if (y < dp.border || y >= h - dp.border || x < dp.border || x >= w - dp.border || layer < 1 ||
+                layer > dp.num_intervals) {
+                alive = false;
+                break;
+            }
+            // no "failed to converge" rejection in the reference: after max_iter
+            // moves the stale cube / grad / hess / upd are used with the moved x, y, layer
+        }
+        if (!alive) continue;
+        const float p0 = grad[0] * upd[0], p1 = grad[1] * upd[1], p2 = grad[2] * upd[2];
+        const float dot = (float)((double)p0 + (double)p1 + (double)p2);  // numpy float32 dot of 3
+        const float val = cube[1][1][1] + 0.5f * dot;
+        if (fabsf(val) * (float)dp.num_intervals < dp.contrast_thr_f) continue;
+        const float tr = hess[0][0] + hess[1][1];
+        // np.linalg.det (LU with partial pivoting in float64, then float32)
+        const double a = hess[0][0], b = hess[0][1], cc = hess[1][0], d = hess[1][1];
+        double det;
+        if (fabs(a) >= fabs(cc)) {
+            if (a == 0.0) det = 0.0;
+            else { const double l = cc / a; det = a * (d - l * b); }
+        } else {
+            const double l = a / cc;
+            det = -(cc * (b - l * d));
+        }
+        const float detf = (float)det;
+        const float er = dp.eigen_ratio_f;
+        if (detf <= 0.f || er * (tr * tr) >= ((er + 1.f) * (er + 1.f)) * detf) continue;
+        Localized L;
+        const float sc = (float)(1 << o);
+        L.x = ((float)x + upd[0]) * sc;
+        L.y = ((float)y + upd[1]) * sc;
+        L.octave_packed = o + layer * 256 + (int)rintf((upd[2] + 0.5f) * 255.f) * 65536;
+        const float e = ((float)layer + upd[2]) / (float)dp.num_intervals;
+        L.size = dp.sigma_f * (float)exp2((double)e) * (float)(1 << (o + 1));
+        L.response = fabsf(val);
+        L.img_o_l = ((uint32_t)img << 16) | ((uint32_t)o << 8) | (uint32_t)layer;
+        L.order = order;
+        const int slot = atomicAdd(&counters[CNT_LOC], 1);
+        atomicAdd(&counters[CNT_HDR + img * CNT_PER_IMG + 1], 1);
+        if (slot < loc_cap) loc[slot] = L;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// orientation assignment (sift_impl.py:246-293), one warp per localized
+// extremum.  Each lane accumulates its share of the (2r+1)^2 window into a
+// private float64 36-bin histogram in shared memory ([bin][lane], bank
+// conflict free); the lanes' histograms are then summed in a fixed order, so
+// the result is deterministic (no atomics).
+// ---------------------------------------------------------------------------
+constexpr int kOriWarps = 4;
+constexpr int kOriMaxBins = 36;
+#define B200_RAD2DEGF (180.0f / 3.141592653589793238462643383279502884f)
+
+__device__ __forceinline__ float mod360f(float a)  // np.float32 % 360 for |a| < 360
+{
+    if (a < 0.f) a += 360.f;
+    else if (a == 0.f) a = 0.f;
+    return a;
+}
+
+__global__ void __launch_bounds__(kOriWarps * 32)
+orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int loc_cap,
+              RawKeypoint *__restrict__ raw, int raw_cap, int32_t *__restrict__ counters)
+{
+    __shared__ double hist_s[kOriWarps][kOriMaxBins][32];
+    __shared__ double raw_s[kOriWarps][kOriMaxBins];
+    __shared__ double smooth_s[kOriWarps][kOriMaxBins];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int nb = dp.ori_bins;  // <= 36
+    const int n = min(counters[CNT_LOC], loc_cap);
+    const int warps_total = gridDim.x * kOriWarps;
+    double(*hist)[32] = hist_s[wib];
+    for (int li = blockIdx.x * kOriWarps + wib; li < n; li += warps_total) {
+        const Localized L = loc[li];
+        const int img = L.img_o_l >> 16, o = (L.img_o_l >> 8) & 255, layer = L.img_o_l & 255;
+        const int h = v.h[o], w = v.w[o], pitch = v.pitch[o];
+        const float *gimg = v.layer(o, layer, img);
+        const float scale = (float)(dp.scale_factor * (double)L.size) / (float)(1 << (o + 1));
+        const int radius = (int)rintf(dp.radius_factor_f * scale);
+        const float weight_fac = -0.5f / (scale * scale);
+        const int cy = (int)rintf(L.y / (float)(1 << o));
+        const int cx = (int)rintf(L.x / (float)(1 << o));
+        for (int b = 0; b < nb; ++b) hist[b][lane] = 0.0;
+        const int side = 2 * radius + 1;
+        const int total = side * side;
+        for (int idx = lane; idx < total; idx += 32) {
+            const int r = idx / side;
+            const int dy = r - radius, dx = idx - r * side - radius;
+            const int y = cy + dy, x = cx + dx;
+            if (x <= 0 || x >= w - 1 || y <= 0 || y >= h - 1) continue;
+            const float *p = gimg + (size_t)y * pitch + x;
+            const float gx = p[1] - p[-1];
+            const float gy = p[-pitch] - p[pitch];
+            const float mag = sqrtf(gx * gx + gy * gy);
+            const float ang = mod360f(atan2f(gy, gx) * B200_RAD2DEGF);
+            const float wgt = expf(weight_fac * (float)(dx * dx + dy * dy));
+            const int bin = (int)rintf(ang * (float)nb / 360.f) % nb;
+            hist[bin][lane] += (double)(wgt * mag);
+        }
+        __syncwarp();
+        for (int b = lane; b < nb; b += 32) {
+            double s = 0.0;
+            for (int l = 0; l < 32; ++l) s += hist[b][(l + lane) & 31];
+            raw_s[wib][b] = s;
+        }
+        __syncwarp();
+        double mx = -1.0;
+        for (int b = lane; b < nb; b += 32) {
+            const double *r = raw_s[wib];
+            const int m1 = (b + nb - 1) % nb, m2 = (b + nb - 2) % nb, p1 = (b + 1) % nb, p2 = (b + 2) % nb;
+            const double s = (6 * r[b] + 4 * (r[m1] + r[p1]) + r[m2] + r[p2]) / 16.;
+            smooth_s[wib][b] = s;
+            mx = fmax(mx, s);
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, sft));
+        __syncwarp();
+        // peaks in ascending bin order; rounds of 32 bins
+        int emitted = 0;
+        for (int b0 = 0; b0 < nb; b0 += 32) {
+            const int b = b0 + lane;
+            bool peak = false;
+            double sl = 0, sr = 0, sc = 0;
+            if (b < nb) {
+                const double *s = smooth_s[wib];
+                sl = s[(b + nb - 1) % nb];
+                sr = s[(b + 1) % nb];
+                sc = s[b];
+                peak = (sc > sl) && (sc > sr) && (sc >= dp.peak_ratio * mx);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, peak);
+            if (m) {
+                int base = 0;
+                if (lane == __ffs(m) - 1) {
+                    base = atomicAdd(&counters[CNT_RAW], __popc(m));
+                    atomicAdd(&counters[CNT_HDR + img * CNT_PER_IMG + 2], __popc(m));
+                }
+                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                if (peak) {
+                    const int slot = base + __popc(m & ((1u << lane) - 1u));
+                    double t = (double)b + 0.5 * (sl - sr) / (sl - 2 * sc + sr);
+                    double interp = fmod(t, (double)nb);
+                    if (interp != 0.0) { if (interp < 0) interp += (double)nb; } else interp = 0.0;
+                    double angle = 360. - interp * 360. / (double)nb;
+                    if (fabs(angle - 360.) < 1e-7) angle = 0;
+                    if (slot < raw_cap) {
+                        RawKeypoint k;
+                        k.x = L.x; k.y = L.y; k.size = L.size; k.angle = (float)angle; k.response = L.response;
+                        k.octave_packed = L.octave_packed;
+                        k.img = img;
+                        k.pad = 0;
+                        k.order = (L.order << 6) | (uint64_t)b;
+                        raw[slot] = k;
+                    }
+                }
+                emitted += __popc(m);
+            }
+        }
+        (void)emitted;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// descriptors (sift_impl.py:349-526), one warp per oriented keypoint.
+// Window pixels are spread over the lanes; each lane scatters its trilinear
+// shares into a private float32 4x4x8 histogram ([bin][lane] in shared
+// memory -- only the inner 4x4 cells of the reference's 6x6 tensor are ever
+// read, :509), the 32 partial histograms are summed in a fixed order, then
+// threshold / normalise / quantise (:512-524) with warp shuffles.
+// ---------------------------------------------------------------------------
+constexpr int kDescWarps = 4;
+
+__global__ void __launch_bounds__(kDescWarps * 32)
+describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw, int n, int converted,
+                uint8_t *__restrict__ desc_out)
+{
+    extern __shared__ float dh_s[];  // [kDescWarps][128][32]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float *hist = dh_s + (size_t)wib * 128 * 32;
+    const int warps_total = gridDim.x * kDescWarps;
+    for (int ki = blockIdx.x * kDescWarps + wib; ki < n; ki += warps_total) {
+        const RawKeypoint K = raw[ki];
+        // convert_keypoints_to_input_image_size (:333-343) unless already done
+        const float kx = converted ? K.x : K.x * 0.5f, ky = converted ? K.y : K.y * 0.5f;
+        const float ksize = converted ? K.size : K.size * 0.5f;
+        const int koct = converted ? K.octave_packed
+                                   : ((K.octave_packed & ~255) | ((K.octave_packed - 1) & 255));
+        // unpack_octave (:349-358)
+        int octv = koct & 255;
+        const int lyr = (koct >> 8) & 255;
+        if (octv >= 128) octv |= -128;
+        const float scl = octv >= 0 ? 1.f / (float)(1 << octv) : (float)(1 << -octv);
+        const int po = octv + 1;
+        bool ok = (po >= 0 && po < v.n_oct && lyr < v.n_layers);
+        const int rows = ok ? v.h[po] : 1, cols = ok ? v.w[po] : 1, pitch = ok ? v.pitch[po] : 1;
+        const float *img = ok ? v.layer(po, lyr, K.img) : nullptr;
+        const int ptx = (int)rint((double)scl * (double)kx);
+        const int pty = (int)rint((double)scl * (double)ky);
+        const double angle = 360. - (double)K.angle;
+        const double rad = angle * (3.14159265358979323846 / 180.0);
+        const double cos_a = cos(rad), sin_a = sin(rad);
+        const float hist_width = (float)dp.scale_multiplier_half * scl * ksize;
+        int half_w = (int)rint((double)hist_width * 1.4142135623730951 * 5 * 0.5);
+        const int diag = (int)sqrt((double)((long long)rows * rows + (long long)cols * cols));
+        half_w = min(half_w, diag);
+        const double hw = (double)hist_width;
+        const float anglef = (float)angle;
+        const float bins_per_deg = (float)(8 / 360.);
+
+        for (int b = 0; b < 128; ++b) hist[b * 32 + lane] = 0.f;
+        const int side = 2 * half_w + 1;
+        const long long total = ok ? (long long)side * side : 0;
+        for (long long idx = lane; idx < total; idx += 32) {
+            const int r = (int)(idx / side);
+            const int ys = r - half_w, xs = (int)(idx - (long long)r * side) - half_w;
+            const int rr = pty + ys, cc = ptx + xs;
+            if (!(rr > 0 && rr < rows - 1 && cc > 0 && cc < cols - 1)) continue;
+            const double r_rot = xs * sin_a + ys * cos_a;
+            const double c_rot = xs * cos_a - ys * sin_a;
+            const double qr = r_rot / hw, qc = c_rot / hw;
+            const double r_bin = qr + 2.0 - 0.5;
+            const double c_bin = qc + 2.0 - 0.5;
+            if (!(r_bin > -1.0 && r_bin < 4.0 && c_bin > -1.0 && c_bin < 4.0)) continue;
+            const float *p = img + (size_t)rr * pitch + cc;
+            const float gx = p[1] - p[-1];
+            const float gy = p[-pitch] - p[pitch];
+            const float mag = sqrtf(gx * gx + gy * gy);
+            const float orient = mod360f(atan2f(gy, gx) * B200_RAD2DEGF);
+            const double wgt = exp(-0.125 * (qr * qr + qc * qc));
+            const double wmag = wgt * (double)mag;
+            float ob = fmodf((orient - anglef) * bins_per_deg, 8.f);  // np.mod(ob, 8) in float32
+            if (ob != 0.f) { if (ob < 0.f) ob += 8.f; } else ob = 0.f;
+            const int r0 = (int)floor(r_bin), c0 = (int)floor(c_bin);
+            int o0 = (int)floorf(ob);
+            o0 = ((o0 % 8) + 8) % 8;
+            const double rf = r_bin - (double)r0, cf = c_bin - (double)c0, of = (double)ob - (double)o0;
+            const double c1 = wmag * rf, c0w = wmag - c1;
+            const double c10 = c1 * (1 - cf), c11 = c1 * cf, c00 = c0w * (1 - cf), c01 = c0w * cf;
+            const int o1 = (o0 + 1) & 7;
+            // inner cells only: tensor index r0+dr+1 in [1,4]  <=>  r0+dr in [0,3]
+#define B200_SCATTER(RB, CB, M)                                              \
+    if ((unsigned)(RB) < 4u && (unsigned)(CB) < 4u) {                        \
+        float *cell = hist + (((RB) * 4 + (CB)) * 8) * 32 + lane;            \
+        cell[o0 * 32] += (float)((M) * (1 - of));                            \
+        cell[o1 * 32] += (float)((M) * of);                                  \
+    }
+            B200_SCATTER(r0, c0, c00)
+            B200_SCATTER(r0, c0 + 1, c01)
+            B200_SCATTER(r0 + 1, c0, c10)
+            B200_SCATTER(r0 + 1, c0 + 1, c11)
+#undef B200_SCATTER
+        }
+        __syncwarp();
+        float vq[4];
+        double ss = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = lane + 32 * q;
+            float s = 0.f;
+            for (int l = 0; l < 32; ++l) s += hist[e * 32 + ((l + lane) & 31)];
+            vq[q] = s;
+            ss += (double)(s * s);
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, sft);
+        const float thr = sqrtf((float)ss) * dp.descriptor_max_value_f;
+        double ss2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (vq[q] > thr) vq[q] = thr;
+            ss2 += (double)(vq[q] * vq[q]);
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) ss2 += __shfl_xor_sync(0xffffffffu, ss2, sft);
+        float norm_v = sqrtf((float)ss2);
+        if (norm_v < 1e-7f) norm_v = 1e-7f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float t = rintf(512.f * (vq[q] / norm_v));
+            t = fminf(fmaxf(t, 0.f), 255.f);
+            desc_out[(size_t)ki * 128 + lane + 32 * q] = (uint8_t)t;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// ordering + de-duplication (sift_impl.py:299-327) + conversion (:333-343)
+// ---------------------------------------------------------------------------
+struct KpLess {
+    const RawKeypoint *raw;
+    int scan_order;
+    __device__ __forceinline__ bool operator()(uint32_t ia, uint32_t ib) const
+    {
+        const RawKeypoint &a = raw[ia], &b = raw[ib];
+        if (a.img != b.img) return a.img < b.img;
+        if (!scan_order) {
+            if (a.x != b.x) return a.x < b.x;
+            if (a.y != b.y) return a.y < b.y;
+            if (a.size != b.size) return a.size > b.size;
+            if (a.angle != b.angle) return a.angle < b.angle;
+            if (a.response != b.response) return a.response > b.response;
+        }
+        return a.order < b.order;  // reference: stable sort of the scan-order list
+    }
+};
+
+__global__ void __launch_bounds__(256) iota_kernel(uint32_t *idx, int n)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) idx[i] = i;
+}
+
+__global__ void __launch_bounds__(256) zero_out_counts_kernel(int32_t *counters, int n_img)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i == 0) counters[CNT_OUT] = 0;
+    if (i < n_img) counters[CNT_HDR + i * CNT_PER_IMG + 3] = 0;
+}
+
+__global__ void __launch_bounds__(256)
+flag_kernel(const RawKeypoint *__restrict__ raw, const uint32_t *__restrict__ idx, int n, int dedupe,
+            uint32_t *__restrict__ keep)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k = 1;
+    if (dedupe && i > 0) {
+        const RawKeypoint &a = raw[idx[i - 1]], &b = raw[idx[i]];
+        if (a.img == b.img && a.x == b.x && a.y == b.y && a.size == b.size && a.angle == b.angle) k = 0;
+    }
+    keep[i] = k;
+}
+
+__global__ void __launch_bounds__(256)
+gather_kernel(const RawKeypoint *__restrict__ raw, const uint8_t *__restrict__ raw_desc,
+              const uint32_t *__restrict__ idx, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ pos,
+              int n, int convert, b200sift_keypoint *__restrict__ kps, uint8_t *__restrict__ desc,
+              int32_t *__restrict__ counters)
+{
+    // 8 threads per keypoint: each moves 16 B of the descriptor
+    const int t = blockIdx.x * 256 + threadIdx.x;
+    const int i = t >> 3, part = t & 7;
+    if (i >= n || !keep[i]) return;
+    const uint32_t src = idx[i], dst = pos[i];
+    if (raw_desc)
+        reinterpret_cast<uint4 *>(desc + (size_t)dst * 128)[part] =
+            reinterpret_cast<const uint4 *>(raw_desc + (size_t)src * 128)[part];
+    if (part == 0) {
+        const RawKeypoint &r = raw[src];
+        b200sift_keypoint k;
+        if (convert) {
+            k.x = r.x * 0.5f; k.y = r.y * 0.5f; k.size = r.size * 0.5f;
+            k.octave = (r.octave_packed & ~255) | ((r.octave_packed - 1) & 255);
+        } else {
+            k.x = r.x; k.y = r.y; k.size = r.size; k.octave = r.octave_packed;
+        }
+        k.angle = r.angle;
+        k.response = r.response;
+        kps[dst] = k;
+        atomicAdd(&counters[CNT_HDR + r.img * CNT_PER_IMG + 3], 1);
+        atomicAdd(&counters[CNT_OUT], 1);
+    }
+}
+
+static int ensure_sparse(b200sift_ctx *c, int cand_cap, int loc_cap, int raw_cap)
+{
+    size_t cap;
+    cap = c->cand_cap; B200_CHECK(ensure(&c->d_cand, &cap, (size_t)cand_cap)); c->cand_cap = (int)cap;
+    cap = c->loc_cap;  B200_CHECK(ensure(&c->d_loc, &cap, (size_t)loc_cap));   c->loc_cap = (int)cap;
+    if (raw_cap > c->raw_cap || !c->d_raw) {
+        cap = c->raw_cap;
+        B200_CHECK(ensure(&c->d_raw, &cap, (size_t)raw_cap));
+        const int rc = (int)cap;
+        size_t cap2 = 0;
+        if (c->d_raw_desc) { cudaFree(c->d_raw_desc); c->d_raw_desc = nullptr; }
+        B200_CHECK(ensure(&c->d_raw_desc, &cap2, (size_t)rc * 128));
+        cap2 = 0; if (c->d_sort_idx) { cudaFree(c->d_sort_idx); c->d_sort_idx = nullptr; }
+        B200_CHECK(ensure(&c->d_sort_idx, &cap2, (size_t)rc));
+        cap2 = 0; if (c->d_keep) { cudaFree(c->d_keep); c->d_keep = nullptr; }
+        B200_CHECK(ensure(&c->d_keep, &cap2, (size_t)rc));
+        cap2 = 0; if (c->d_pos) { cudaFree(c->d_pos); c->d_pos = nullptr; }
+        B200_CHECK(ensure(&c->d_pos, &cap2, (size_t)rc));
+        cap2 = 0; if (c->d_kps) { cudaFree(c->d_kps); c->d_kps = nullptr; }
+        B200_CHECK(ensure(&c->d_kps, &cap2, (size_t)rc));
+        cap2 = 0; if (c->d_desc) { cudaFree(c->d_desc); c->d_desc = nullptr; }
+        B200_CHECK(ensure(&c->d_desc, &cap2, (size_t)rc * 128));
+        c->raw_cap = rc;
+        c->out_cap = rc;
+    }
+    return 0;
+}
+
+static int ensure_counters(b200sift_ctx *c, int n_img)
+{
+    const int need = CNT_HDR + n_img * CNT_PER_IMG;
+    if (need > c->counters_len) {
+        if (c->d_counters) cudaFree(c->d_counters);
+        if (c->h_counters) cudaFreeHost(c->h_counters);
+        B200_CUDA(cudaMalloc((void **)&c->d_counters, sizeof(int32_t) * need));
+        B200_CUDA(cudaMallocHost((void **)&c->h_counters, sizeof(int32_t) * need));
+        c->counters_len = need;
+    }
+    return 0;
+}
+
+// extrema -> refine -> orientation on the context's pyramid.  Leaves the raw
+// (unsorted) oriented keypoints in c->d_raw and the counters on the host.
+int run_detect(b200sift_ctx *c, const b200sift_params &p, int /*want_scan_order*/)
+{
+    const Pyramid &py = c->pyr;
+    B200_ARG(p.num_intervals >= 1 && p.num_intervals + 3 == py.n_layers);
+    B200_ARG(p.image_border_width >= 1);
+    B200_ARG(p.ori_bins >= 4 && p.ori_bins <= kOriMaxBins);
+    B200_ARG(p.max_iter >= 1);
+    B200_ARG(py.h[0] < 32768 && py.w[0] < 32768 && py.n_img < 65536);
+    const PyrView v = make_view(py);
+    const DetectParams dp = make_detect_params(p);
+    B200_CHECK(ensure_counters(c, py.n_img));
+    const size_t px = (size_t)py.n_img * py.h[0] * py.w[0];
+    int cand_cap = (int)(px / 48 + 16384), loc_cap = (int)(px / 96 + 8192), raw_cap = (int)(px / 64 + 8192);
+    if (c->cand_cap > cand_cap) cand_cap = c->cand_cap;
+    if (c->loc_cap > loc_cap) loc_cap = c->loc_cap;
+    if (c->raw_cap > raw_cap) raw_cap = c->raw_cap;
+    const int n_cnt = CNT_HDR + py.n_img * CNT_PER_IMG;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        B200_CHECK(ensure_sparse(c, cand_cap, loc_cap, raw_cap));
+        B200_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(int32_t) * n_cnt, c->stream));
+        const size_t ex_smem = (size_t)(py.n_layers - 1) * (kExTW + 2) * (kExTH + 2) * sizeof(float);
+        for (int o = 0; o < py.n_oct; ++o) {
+            const int sh = py.h[o] - 2 * p.image_border_width, sw = py.w[o] - 2 * p.image_border_width;
+            if (sh <= 0 || sw <= 0) continue;
+            dim3 grid((sw + kExTW - 1) / kExTW, (sh + kExTH - 1) / kExTH, py.n_img);
+            extrema_kernel<<<grid, 256, ex_smem, c->stream>>>(v, o, p.image_border_width, p.num_intervals,
+                                                              dp.dog_thresh, c->d_cand, c->cand_cap, c->d_counters);
+            c->launches++;
+        }
+        B200_CUDA(cudaGetLastError());
+        {
+            int blocks = (c->cand_cap + 127) / 128;
+            if (blocks > c->sm_count * 8) blocks = c->sm_count * 8;
+            refine_kernel<<<blocks, 128, 0, c->stream>>>(v, dp, c->d_cand, c->cand_cap, c->d_loc, c->loc_cap,
+                                                         c->d_counters);
+            c->launches++;
+            orient_kernel<<<c->sm_count * 4, kOriWarps * 32, 0, c->stream>>>(v, dp, c->d_loc, c->loc_cap, c->d_raw,
+                                                                             c->raw_cap, c->d_counters);
+            c->launches++;
+        }
+        B200_CUDA(cudaGetLastError());
+        B200_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int32_t) * n_cnt, cudaMemcpyDeviceToHost,
+                                  c->stream));
+        B200_CUDA(cudaStreamSynchronize(c->stream));
+        const int nc = c->h_counters[CNT_CAND], nl = c->h_counters[CNT_LOC], nr = c->h_counters[CNT_RAW];
+        if (nc <= c->cand_cap && nl <= c->loc_cap && nr <= c->raw_cap) return 0;
+        // a fixed-capacity list overflowed: grow to twice what was needed and redo the stage
+        if (nc > c->cand_cap) cand_cap = 2 * nc;
+        if (nl > c->loc_cap) loc_cap = 2 * nl;
+        if (nr > c->raw_cap) raw_cap = 2 * nr + 1024;
+        if (nc > c->cand_cap && loc_cap < nc) loc_cap = nc;
+        if (raw_cap < 2 * loc_cap) raw_cap = 2 * loc_cap;
+    }
+    set_error("keypoint buffers still overflow after 4 attempts");
+    return B200SIFT_ECAPACITY;
+}
+
+int run_describe(b200sift_ctx *c, const b200sift_params &p, const RawKeypoint *d_raw, int n, int converted,
+                 uint8_t *d_out)
+{
+    if (n <= 0) return 0;
+    B200_ARG(p.window_width == 4 && p.desc_bins == 8);
+    const PyrView v = make_view(c->pyr);
+    const DetectParams dp = make_detect_params(p);
+    const size_t smem = (size_t)kDescWarps * 128 * 32 * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+        B200_CUDA(cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    int blocks = (n + kDescWarps - 1) / kDescWarps;
+    if (blocks > c->sm_count * 3 * 4) blocks = c->sm_count * 3 * 4;
+    describe_kernel<<<blocks, kDescWarps * 32, smem, c->stream>>>(v, dp, d_raw, n, converted, d_out);
+    c->launches++;
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Sort the n raw keypoints (by image, then compare_keypoints or scan order),
+// optionally drop duplicates, convert and compact into c->d_kps / c->d_desc.
+int run_sort_gather(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int dedupe, int convert, int with_desc)
+{
+    B200_CHECK(ensure_counters(c, n_img));
+    c->img_off.assign(n_img + 1, 0);
+    if (n_raw <= 0) return 0;
+    const int blocks = (n_raw + 255) / 256;
+    iota_kernel<<<blocks, 256, 0, c->stream>>>(c->d_sort_idx, n_raw);
+    c->launches++;
+    KpLess less{c->d_raw, scan_order};
+    size_t tmp = 0;
+    B200_CUDA(cub::DeviceMergeSort::StableSortKeys(nullptr, tmp, c->d_sort_idx, n_raw, less, c->stream));
+    size_t tmp2 = 0;
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, c->d_keep, c->d_pos, n_raw, c->stream));
+    if (tmp2 > tmp) tmp = tmp2;
+    if (tmp > c->cub_tmp_cap) {
+        if (c->d_cub_tmp) cudaFree(c->d_cub_tmp);
+        c->d_cub_tmp = nullptr;
+        B200_CUDA(cudaMalloc(&c->d_cub_tmp, tmp + 1024));
+        c->cub_tmp_cap = tmp + 1024;
+    }
+    size_t t1 = c->cub_tmp_cap;
+    B200_CUDA(cub::DeviceMergeSort::StableSortKeys(c->d_cub_tmp, t1, c->d_sort_idx, n_raw, less, c->stream));
+    c->launches += 2;
+    zero_out_counts_kernel<<<(n_img + 255) / 256, 256, 0, c->stream>>>(c->d_counters, n_img);
+    flag_kernel<<<blocks, 256, 0, c->stream>>>(c->d_raw, c->d_sort_idx, n_raw, dedupe, c->d_keep);
+    t1 = c->cub_tmp_cap;
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub_tmp, t1, c->d_keep, c->d_pos, n_raw, c->stream));
+    gather_kernel<<<(n_raw * 8 + 255) / 256, 256, 0, c->stream>>>(c->d_raw, with_desc ? c->d_raw_desc : nullptr,
+                                                                  c->d_sort_idx, c->d_keep, c->d_pos, n_raw, convert,
+                                                                  c->d_kps, c->d_desc, c->d_counters);
+    c->launches += 4;
+    B200_CUDA(cudaGetLastError());
+    const int n_cnt = CNT_HDR + n_img * CNT_PER_IMG;
+    B200_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int32_t) * n_cnt, cudaMemcpyDeviceToHost,
+                              c->stream));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n_img; ++i) c->img_off[i + 1] = c->img_off[i] + c->h_counters[CNT_HDR + i * CNT_PER_IMG + 3];
+    return 0;
+}
+
+int ensure_sparse_for(b200sift_ctx *c, int n_img, int n_raw)
+{
+    B200_CHECK(ensure_counters(c, n_img));
+    return ensure_sparse(c, c->cand_cap > 0 ? c->cand_cap : 1024, c->loc_cap > 0 ? c->loc_cap : 1024,
+                         n_raw > c->raw_cap ? n_raw : c->raw_cap);
+}
+
+// ---------------------------------------------------------------------------
+// "next" rows f1 / f2
+// ---------------------------------------------------------------------------
+
+// ransac() vote (image_stitching_sift.py:86-111): one thread per candidate
+// shift counts the matches within dist_sq_thresh (float64, as the python
+// floats of the reference); the first maximum wins.
+__global__ void __launch_bounds__(256)
+ransac_vote_kernel(const float *__restrict__ m, int n, double thr, int32_t *__restrict__ votes)
+{
+    extern __shared__ double sh[];  // [n][2] candidate moves
+    for (int j = threadIdx.x; j < n; j += 256) {
+        sh[2 * j] = (double)m[4 * j] - (double)m[4 * j + 2];
+        sh[2 * j + 1] = (double)m[4 * j + 1] - (double)m[4 * j + 3];
+    }
+    __syncthreads();
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const double dxr = sh[2 * i], dyr = sh[2 * i + 1];
+        int cnt = 0;
+        for (int j = 0; j < n; ++j) {
+            const double dx = sh[2 * j] - dxr, dy = sh[2 * j + 1] - dyr;
+            cnt += (dx * dx + dy * dy < thr) ? 1 : 0;
+        }
+        votes[i] = cnt;
+    }
+}
+
+__global__ void __launch_bounds__(256) ransac_pick_kernel(const int32_t *__restrict__ votes, int n, int32_t *best)
+{
+    // first maximum: maximise (votes << 32) | (~index)
+    __shared__ unsigned long long red[256];
+    unsigned long long k = 0;
+    for (int i = threadIdx.x; i < n; i += 256) {
+        const unsigned long long key = ((unsigned long long)(uint32_t)votes[i] << 32) | (uint32_t)(~(uint32_t)i);
+        if (key > k) k = key;
+    }
+    red[threadIdx.x] = k;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (threadIdx.x < s && red[threadIdx.x + s] > red[threadIdx.x]) red[threadIdx.x] = red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        best[0] = (int32_t)(~(uint32_t)(red[0] & 0xffffffffu));
+        best[1] = (int32_t)(red[0] >> 32);
+    }
+}
+
+int launch_ransac(b200sift_ctx *c, const float *d_matches, int n, double thr, double *move, int32_t *best)
+{
+    move[0] = move[1] = 0;
+    *best = -1;
+    if (n <= 0) return 0;
+    B200_ARG(n <= 12000);  // candidate moves live in shared memory (16 B each)
+    size_t cap = c->misc_cap;
+    B200_CHECK(ensure((uint8_t **)&c->d_misc, &cap, (size_t)(n + 8) * sizeof(int32_t)));
+    c->misc_cap = cap;
+    int32_t *votes = (int32_t *)c->d_misc;
+    const size_t smem = (size_t)n * 2 * sizeof(double);
+    static size_t attr_smem = 48 * 1024;
+    if (smem > attr_smem) {
+        B200_CUDA(cudaFuncSetAttribute(ransac_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    const int blocks = (n + 255) / 256;
+    ransac_vote_kernel<<<blocks, 256, smem, c->stream>>>(d_matches, n, thr, votes);
+    ransac_pick_kernel<<<1, 256, 0, c->stream>>>(votes, n, votes + n);
+    c->launches += 2;
+    B200_CUDA(cudaGetLastError());
+    int32_t res[2];
+    B200_CUDA(cudaMemcpyAsync(res, votes + n, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
+    float mm[4];
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(cudaMemcpy(mm, d_matches + 4 * (size_t)res[0], sizeof(mm), cudaMemcpyDeviceToHost));
+    *best = res[0];
+    move[0] = (double)mm[0] - (double)mm[2];
+    move[1] = (double)mm[1] - (double)mm[3];
+    return 0;
+}
+
+// cylindrical_projection (image_stitching_sift.py:117-136).  The reference is
+// a forward map where later source pixels (row-major) overwrite earlier ones;
+// here every source pixel publishes its row-major index with atomicMax into a
+// per-destination winner map, then each destination copies from its winner.
+__global__ void __launch_bounds__(256) cyl_winner_kernel(int h, int w, double f, int32_t *__restrict__ winner)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= h * w) return;
+    const int yy = i / w, xx = i - yy * w;
+    const int xd = xx - w / 2, yd = yy - h / 2;
+    const long long xm = (long long)rint(f * atan((double)xd / f)) + w / 2;
+    const double denom = sqrt((double)(xd * xd) + f * f);
+    const long long ym = (long long)rint(f * ((double)yd / denom)) + h / 2;
+    if (xm >= 0 && xm < w && ym >= 0 && ym < h) atomicMax(&winner[ym * w + xm], i);
+}
+
+__global__ void __launch_bounds__(256)
+cyl_copy_kernel(const uint8_t *__restrict__ src, int n, int ch, const int32_t *__restrict__ winner,
+                uint8_t *__restrict__ dst)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int s = winner[i];
+    for (int k = 0; k < ch; ++k) dst[(size_t)i * ch + k] = s >= 0 ? src[(size_t)s * ch + k] : 0;
+}
+
+int launch_cyl(b200sift_ctx *c, const uint8_t *d_src, int h, int w, int ch, double f, uint8_t *d_dst)
+{
+    const int n = h * w;
+    size_t cap = c->misc_cap;
+    B200_CHECK(ensure((uint8_t **)&c->d_misc, &cap, (size_t)n * sizeof(int32_t)));
+    c->misc_cap = cap;
+    int32_t *winner = (int32_t *)c->d_misc;
+    B200_CUDA(cudaMemsetAsync(winner, 0xff, (size_t)n * sizeof(int32_t), c->stream));
+    cyl_winner_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(h, w, f, winner);
+    cyl_copy_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_src, n, ch, winner, d_dst);
+    c->launches += 2;
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b200

@@ -1,0 +1,486 @@
+// Dense front-end of the SIFT path: grey conversion + 2x upsample, separable
+// Gaussian blur (HBM-bound strip kernel + generic tile kernel), octave
+// decimation, DoG materialisation for the stage API.
+//
+// Replaces (all in /root/reference): sift_impl.py:27-29 (cv2.cvtColor + float
+// cast), :45-56 generate_base_image (cv2.resize INTER_LINEAR + GaussianBlur),
+// :82-97 generate_gaussian_images (incremental cv2.GaussianBlur chain +
+// INTER_NEAREST decimation), :100-111 generate_DoG_images.
+#include <math.h>
+#include "common.cuh"
+
+namespace b200 {
+
+// Up to 16 tap sets (centre..R) resident in constant memory; a launch names
+// its set.  Set 15 is reserved for the stand-alone blur entry point.
+__constant__ float c_taps[16][kMaxBlurRadius + 1];
+
+struct TapCache {
+    double sigma[16];
+    int radius[16];
+    bool valid[16];
+};
+static TapCache g_taps[16];  // per device ordinal
+
+// cv2.getGaussianKernel(ksize, sigma, CV_32F) with ksize = cvRound(8*sigma+1)|1
+// (the CV_32F branch of cv::createGaussianKernels): taps = float(exp(-x^2/2s^2)/sum).
+static int gaussian_taps(double sigma, float *taps /*centre..R*/)
+{
+    int ks = ((int)rint(sigma * 8.0 + 1.0)) | 1;
+    int r = ks / 2;
+    if (r > kMaxBlurRadius) return -1;
+    double tmp[2 * kMaxBlurRadius + 1], sum = 0, s2 = -0.5 / (sigma * sigma);
+    for (int i = 0; i < ks; ++i) {
+        double x = i - (ks - 1) * 0.5;
+        tmp[i] = exp(s2 * x * x);
+        sum += tmp[i];
+    }
+    sum = 1.0 / sum;
+    for (int k = 0; k <= r; ++k) taps[k] = (float)(tmp[r + k] * sum);
+    return r;
+}
+
+static int upload_taps(b200sift_ctx *c, int set, double sigma, int *radius)
+{
+    TapCache &tc = g_taps[c->device & 15];
+    if (tc.valid[set] && tc.sigma[set] == sigma) {
+        *radius = tc.radius[set];
+        return 0;
+    }
+    float taps[kMaxBlurRadius + 1] = {0};
+    int r = gaussian_taps(sigma, taps);
+    if (r < 0) {
+        set_error("sigma %.3f needs a blur radius > %d", sigma, kMaxBlurRadius);
+        return B200SIFT_EARG;
+    }
+    // Synchronous copy (pageable source buffer lives on this stack frame); ordered
+    // after earlier launches that may still read the set.
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(cudaMemcpyToSymbol(c_taps, taps, sizeof(taps), (size_t)set * sizeof(taps)));
+    tc.valid[set] = true;
+    tc.sigma[set] = sigma;
+    tc.radius[set] = r;
+    *radius = r;
+    return 0;
+}
+
+// cv::borderInterpolate(BORDER_REFLECT_101)
+__device__ __forceinline__ int reflect101(int p, int len)
+{
+    if ((unsigned)p < (unsigned)len) return p;
+    if (len == 1) return 0;
+    do {
+        p = p < 0 ? -p : 2 * (len - 1) - p;
+    } while ((unsigned)p >= (unsigned)len);
+    return p;
+}
+
+// ---------------------------------------------------------------------------
+// grey + 2x bilinear upsample: (u8 BGR | u8 grey | f32 grey) -> f32 (2h x 2w)
+// cv2.cvtColor fixed point (B*3735 + G*19235 + R*9798 + 16384) >> 15, then
+// cv2.resize INTER_LINEAR fx=fy=2: src = (dst+0.5)/2 - 0.5, weights .25/.75,
+// replicate clamp, horizontal pass first.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float load_grey(const uint8_t *img, size_t row_stride, int y, int x, int channels,
+                                           int dtype)
+{
+    const uint8_t *row = img + (size_t)y * row_stride;
+    if (dtype == B200SIFT_F32) return reinterpret_cast<const float *>(row)[x];
+    if (channels == 1) return (float)row[x];
+    const uint8_t *p = row + 3 * x;
+    return (float)((p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + 16384) >> 15);
+}
+
+__global__ void __launch_bounds__(256) gray_upsample_kernel(const uint8_t *__restrict__ in, size_t img_stride_bytes,
+                                                            size_t row_stride, int h, int w, int channels, int dtype,
+                                                            float *__restrict__ out, int out_pitch)
+{
+    const int X = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (X >= 2 * w || Y >= 2 * h) return;
+    const uint8_t *img = in + (size_t)blockIdx.z * img_stride_bytes;
+    int sx = (X & 1) ? (X >> 1) : (X >> 1) - 1;
+    float fx = (X & 1) ? 0.25f : 0.75f;
+    if (sx < 0) { sx = 0; fx = 0.f; }
+    int sx1 = sx + 1;
+    if (sx >= w - 1) { sx = w - 1; sx1 = w - 1; fx = 0.f; }
+    int sy = (Y & 1) ? (Y >> 1) : (Y >> 1) - 1;
+    float fy = (Y & 1) ? 0.25f : 0.75f;
+    if (sy < 0) { sy = 0; fy = 0.f; }
+    int sy1 = sy + 1;
+    if (sy >= h - 1) { sy = h - 1; sy1 = h - 1; fy = 0.f; }
+    float a = load_grey(img, row_stride, sy, sx, channels, dtype);
+    float b = load_grey(img, row_stride, sy, sx1, channels, dtype);
+    float c = load_grey(img, row_stride, sy1, sx, channels, dtype);
+    float d = load_grey(img, row_stride, sy1, sx1, channels, dtype);
+    float r0 = __fadd_rn(__fmul_rn(a, 1.f - fx), __fmul_rn(b, fx));
+    float r1 = __fadd_rn(__fmul_rn(c, 1.f - fx), __fmul_rn(d, fx));
+    float v = __fadd_rn(__fmul_rn(r0, 1.f - fy), __fmul_rn(r1, fy));
+    out[(size_t)blockIdx.z * (size_t)(2 * h) * out_pitch + (size_t)Y * out_pitch + X] = v;
+}
+
+int launch_gray_upsample(b200sift_ctx *c, const void *d_in, size_t img_stride_bytes, size_t row_stride, int n_img,
+                         int h, int w, int channels, int dtype, float *d_out, int out_pitch)
+{
+    dim3 grid((2 * w + 31) / 32, (2 * h + 7) / 8, n_img);
+    gray_upsample_kernel<<<grid, 256, 0, c->stream>>>((const uint8_t *)d_in, img_stride_bytes, row_stride, h, w,
+                                                      channels, dtype, d_out, out_pitch);
+    c->launches++;
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Separable Gaussian blur, strip kernel.
+//
+// One CTA owns a 256-column strip of `seg_rows` output rows of one image and
+// marches down it in batches of 8 rows:
+//   global -> (register prefetch) -> in_s[8][256+2RP]      raw rows + x halo
+//   row pass, 4 adjacent outputs per thread from float4 LDS -> ring[2R+8][256]
+//   column pass, one column x 8 rows per thread from the ring -> global
+// Every input float is read once from HBM (+ 2RP/256 halo from L2, + 2R/seg
+// rows of y halo) and every output written once: 8 B per pixel.  The optional
+// dst2 receives the [::2, ::2] decimation that seeds the next octave
+// (sift_impl.py:95-96), saving a separate pass.
+// Arithmetic: k0*c + sum_k k[k]*(a[+k] + a[-k]) in float32 (fmaf), rows then
+// columns, BORDER_REFLECT_101 -- the structure of OpenCV's symmetric
+// separable float filter.
+// ---------------------------------------------------------------------------
+constexpr int kStripW = 256;
+constexpr int kStripBR = 8;
+
+template <int R>
+__global__ void __launch_bounds__(256, 2)
+blur_strip_kernel(const float *__restrict__ src, float *__restrict__ dst, float *__restrict__ dst2, int h, int w,
+                  int pitch, size_t img_stride, int h2, int w2, int pitch2, size_t img_stride2, int seg_rows,
+                  int tapset)
+{
+    constexpr int TW = kStripW, BR = kStripBR;
+    constexpr int RP = (R + 3) & ~3;
+    constexpr int INW = TW + 2 * RP;
+    constexpr int RING = 2 * R + BR;
+    constexpr int NV4 = BR * INW / 4;            // float4 slots of one input batch
+    constexpr int NV = (NV4 + 255) / 256;        // per thread
+    extern __shared__ __align__(16) float smem[];
+    float *in_s = smem;                // [BR][INW]
+    float *ring = smem + BR * INW;     // [RING][TW]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x0 = blockIdx.x * TW;
+    const int ys = blockIdx.y * seg_rows;
+    const int ye = min(ys + seg_rows, h);
+    src += (size_t)blockIdx.z * img_stride;
+    dst += (size_t)blockIdx.z * img_stride;
+    if (dst2) dst2 += (size_t)blockIdx.z * img_stride2;
+
+    float taps[R + 1];
+#pragma unroll
+    for (int k = 0; k <= R; ++k) taps[k] = c_taps[tapset][k];
+
+    float4 pre[NV];
+    auto gload = [&](int yb) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int f = tid + i * 256;
+            if (f < NV4) {
+                const int row = f / (INW / 4), c4 = f - row * (INW / 4);
+                const int y = reflect101(yb + row, h);
+                const int x = x0 - RP + 4 * c4;
+                const float *p = src + (size_t)y * pitch;
+                if (x >= 0 && x + 3 < w) {
+                    pre[i] = *reinterpret_cast<const float4 *>(p + x);
+                } else {
+                    pre[i].x = p[reflect101(x, w)];
+                    pre[i].y = p[reflect101(x + 1, w)];
+                    pre[i].z = p[reflect101(x + 2, w)];
+                    pre[i].w = p[reflect101(x + 3, w)];
+                }
+            }
+        }
+    };
+    auto sstore = [&]() {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int f = tid + i * 256;
+            if (f < NV4) reinterpret_cast<float4 *>(in_s)[f] = pre[i];
+        }
+    };
+
+    const int n_batches = (ye - ys + 2 * R + BR - 1) / BR;
+    gload(ys - R);
+    int ring_base = 0;  // slot of the first h-row of the current batch
+    for (int b = 0; b < n_batches; ++b) {
+        sstore();
+        __syncthreads();
+        if (b + 1 < n_batches) gload(ys - R + (b + 1) * BR);
+
+        // ---- row pass: warp <-> batch row, 2 groups of 4 adjacent columns per lane
+        {
+            const float *rowp = in_s + warp * INW;
+            int slot = ring_base + warp;
+            if (slot >= RING) slot -= RING;
+            float *outp = ring + slot * TW;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const int cidx = g * 128 + 4 * lane;
+                float v[4 + 2 * RP];
+#pragma unroll
+                for (int q = 0; q < (4 + 2 * RP) / 4; ++q) {
+                    const float4 t = *reinterpret_cast<const float4 *>(rowp + cidx + 4 * q);
+                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                }
+                float4 o;
+                float *op = reinterpret_cast<float *>(&o);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float acc = taps[0] * v[j + RP];
+#pragma unroll
+                    for (int k = 1; k <= R; ++k) acc = fmaf(taps[k], v[j + RP + k] + v[j + RP - k], acc);
+                    op[j] = acc;
+                }
+                *reinterpret_cast<float4 *>(outp + cidx) = o;
+            }
+        }
+        __syncthreads();
+
+        // ---- column pass: thread <-> column, BR output rows
+        const int yo0 = ys + b * BR - 2 * R;  // output row of t = 0
+        if (yo0 + BR - 1 >= ys) {
+            int base = ring_base + BR;        // oldest slot
+            if (base >= RING) base -= RING;
+            float vals[RING];
+#pragma unroll
+            for (int i = 0; i < RING; ++i) {
+                int s = base + i;
+                if (s >= RING) s -= RING;
+                vals[i] = ring[s * TW + tid];
+            }
+            const int x = x0 + tid;
+#pragma unroll
+            for (int t = 0; t < BR; ++t) {
+                float acc = taps[0] * vals[t + R];
+#pragma unroll
+                for (int k = 1; k <= R; ++k) acc = fmaf(taps[k], vals[t + R + k] + vals[t + R - k], acc);
+                const int yo = yo0 + t;
+                if (yo >= ys && yo < ye && x < w) {
+                    dst[(size_t)yo * pitch + x] = acc;
+                    if (dst2 && !((yo | x) & 1) && (yo >> 1) < h2 && (x >> 1) < w2)
+                        dst2[(size_t)(yo >> 1) * pitch2 + (x >> 1)] = acc;
+                }
+            }
+        }
+        ring_base += BR;
+        if (ring_base >= RING) ring_base -= RING;
+        // the next iteration's first barrier orders this column pass before the
+        // row pass that overwrites the oldest ring slots.
+    }
+}
+
+// Generic tile kernel: any radius <= kMaxBlurRadius, any (tiny) image.
+// 32x32 output tile per CTA, halo tile in shared memory, same arithmetic.
+__global__ void __launch_bounds__(256)
+blur_tile_kernel(const float *__restrict__ src, float *__restrict__ dst, float *__restrict__ dst2, int h, int w,
+                 int pitch, size_t img_stride, int h2, int w2, int pitch2, size_t img_stride2, int R, int tapset)
+{
+    constexpr int T = 32;
+    extern __shared__ __align__(16) float smem[];
+    const int IW = T + 2 * R;
+    float *in_s = smem;            // [IW][IW]
+    float *hs = smem + IW * IW;    // [IW][T]
+    const int x0 = blockIdx.x * T, y0 = blockIdx.y * T;
+    src += (size_t)blockIdx.z * img_stride;
+    dst += (size_t)blockIdx.z * img_stride;
+    if (dst2) dst2 += (size_t)blockIdx.z * img_stride2;
+    for (int i = threadIdx.x; i < IW * IW; i += 256) {
+        const int yy = i / IW, xx = i - yy * IW;
+        in_s[i] = src[(size_t)reflect101(y0 - R + yy, h) * pitch + reflect101(x0 - R + xx, w)];
+    }
+    __syncthreads();
+    const float *taps = c_taps[tapset];
+    for (int i = threadIdx.x; i < IW * T; i += 256) {
+        const int yy = i / T, cx = i - yy * T;
+        const float *p = in_s + yy * IW + cx + R;
+        float acc = taps[0] * p[0];
+        for (int k = 1; k <= R; ++k) acc = fmaf(taps[k], p[k] + p[-k], acc);
+        hs[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < T * T; i += 256) {
+        const int r = i / T, cx = i - r * T;
+        const int y = y0 + r, x = x0 + cx;
+        if (y >= h || x >= w) continue;
+        const float *p = hs + (r + R) * T + cx;
+        float acc = taps[0] * p[0];
+        for (int k = 1; k <= R; ++k) acc = fmaf(taps[k], p[k * T] + p[-k * T], acc);
+        dst[(size_t)y * pitch + x] = acc;
+        if (dst2 && !((y | x) & 1) && (y >> 1) < h2 && (x >> 1) < w2)
+            dst2[(size_t)(y >> 1) * pitch2 + (x >> 1)] = acc;
+    }
+}
+
+template <int R>
+static int launch_strip(b200sift_ctx *c, const float *src, float *dst, float *dst2, int n_img, int h, int w,
+                        int pitch, size_t img_stride, int h2, int w2, int pitch2, size_t img_stride2, int tapset)
+{
+    constexpr int RP = (R + 3) & ~3;
+    const size_t smem = (size_t)(kStripBR * (kStripW + 2 * RP) + (2 * R + kStripBR) * kStripW) * sizeof(float);
+    const int strips = (w + kStripW - 1) / kStripW;
+    // enough CTAs for >= 2 per SM, segments of >= 64 rows (y-halo re-read <= 2R/64)
+    const int want = (2 * c->sm_count + strips * n_img - 1) / (strips * n_img);
+    int seg = (h + want - 1) / want;
+    seg = ((seg + kStripBR - 1) / kStripBR) * kStripBR;
+    if (seg < 64) seg = 64;
+    if (seg > 512) seg = 512;
+    dim3 grid(strips, (h + seg - 1) / seg, n_img);
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+        B200_CUDA(cudaFuncSetAttribute(blur_strip_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    blur_strip_kernel<R><<<grid, 256, smem, c->stream>>>(src, dst, dst2, h, w, pitch, img_stride, h2, w2, pitch2,
+                                                         img_stride2, seg, tapset);
+    c->launches++;
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int launch_blur_set(b200sift_ctx *c, const float *src, float *dst, int n_img, int h, int w, int pitch,
+                           size_t img_stride, int R, int tapset, float *dst2, int h2, int w2, int pitch2,
+                           size_t img_stride2)
+{
+    const bool strip_ok = (w >= 96) && (h >= 32) && (pitch % 4 == 0) &&
+                          ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (img_stride % 4 == 0);
+    if (strip_ok) {
+        switch (R) {
+#define B200_STRIP(RR)                                                                                         \
+    case RR:                                                                                                   \
+        return launch_strip<RR>(c, src, dst, dst2, n_img, h, w, pitch, img_stride, h2, w2, pitch2, img_stride2, \
+                                tapset);
+            B200_STRIP(5)
+            B200_STRIP(6)
+            B200_STRIP(8)
+            B200_STRIP(10)
+            B200_STRIP(13)
+#undef B200_STRIP
+            default: break;
+        }
+    }
+    const int IW = 32 + 2 * R;
+    const size_t smem = (size_t)(IW * IW + IW * 32) * sizeof(float);
+    static size_t attr_smem = 48 * 1024;
+    if (smem > attr_smem) {
+        B200_CUDA(cudaFuncSetAttribute(blur_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    dim3 grid((w + 31) / 32, (h + 31) / 32, n_img);
+    blur_tile_kernel<<<grid, 256, smem, c->stream>>>(src, dst, dst2, h, w, pitch, img_stride, h2, w2, pitch2,
+                                                     img_stride2, R, tapset);
+    c->launches++;
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_blur(b200sift_ctx *c, const float *src, float *dst, int n_img, int h, int w, int pitch, size_t img_stride,
+                double sigma, float *dst2, int h2, int w2, int pitch2, size_t img_stride2)
+{
+    int R;
+    B200_CHECK(upload_taps(c, 15, sigma, &R));
+    return launch_blur_set(c, src, dst, n_img, h, w, pitch, img_stride, R, 15, dst2, h2, w2, pitch2, img_stride2);
+}
+
+// ---------------------------------------------------------------------------
+// pyramid layout + octave builder
+// ---------------------------------------------------------------------------
+int pyramid_layout(b200sift_ctx *c, int n_img, int h0, int w0, int n_oct, int n_layers)
+{
+    B200_ARG(n_img >= 1 && h0 >= 1 && w0 >= 1);
+    B200_ARG(n_oct >= 1 && n_oct <= kMaxOctaves);
+    B200_ARG(n_layers >= 4 && n_layers <= kMaxLayers);
+    Pyramid &p = c->pyr;
+    p.n_img = n_img;
+    p.n_oct = n_oct;
+    p.n_layers = n_layers;
+    size_t off = 0;
+    int h = h0, w = w0;
+    for (int o = 0; o < n_oct; ++o) {
+        if (h < 1 || w < 1) {
+            set_error("octave %d of a %dx%d base image is empty", o, h0, w0);
+            return B200SIFT_EARG;
+        }
+        p.h[o] = h;
+        p.w[o] = w;
+        p.pitch[o] = (w + 7) & ~7;
+        p.oct_off[o] = off;
+        off += (size_t)n_layers * n_img * h * p.pitch[o];
+        off = (off + 63) & ~(size_t)63;
+        h /= 2;
+        w /= 2;
+    }
+    p.floats = off;
+    if (off > p.capacity_floats || !p.base) {
+        float *nb = p.base;
+        size_t cap = p.capacity_floats;
+        B200_CHECK(ensure(&nb, &cap, off));
+        p.base = nb;
+        p.capacity_floats = cap;
+    }
+    return 0;
+}
+
+// generate_gaussian_images (sift_impl.py:82-97): layer 0 of octave 0 must be
+// present; builds every other layer.  sigmas[l] is the incremental sigma of
+// layer l (index 0 unused).
+int build_octaves(b200sift_ctx *c, const double *sigmas)
+{
+    Pyramid &p = c->pyr;
+    int R[kMaxLayers];
+    for (int l = 1; l < p.n_layers; ++l) B200_CHECK(upload_taps(c, l, sigmas[l], &R[l]));
+    for (int o = 0; o < p.n_oct; ++o) {
+        for (int l = 1; l < p.n_layers; ++l) {
+            float *dst2 = nullptr;
+            int h2 = 0, w2 = 0, pitch2 = 0;
+            size_t is2 = 0;
+            if (l == p.n_layers - 3 && o + 1 < p.n_oct) {
+                dst2 = p.layer(o + 1, 0);
+                h2 = p.h[o + 1];
+                w2 = p.w[o + 1];
+                pitch2 = p.pitch[o + 1];
+                is2 = p.img_stride(o + 1);
+            }
+            B200_CHECK(launch_blur_set(c, p.layer(o, l - 1), p.layer(o, l), p.n_img, p.h[o], p.w[o], p.pitch[o],
+                                       p.img_stride(o), R[l], l, dst2, h2, w2, pitch2, is2));
+        }
+    }
+    return 0;
+}
+
+int base_blur(b200sift_ctx *c, const float *d_up, double sigma_diff)
+{
+    Pyramid &p = c->pyr;
+    int R;
+    B200_CHECK(upload_taps(c, 0, sigma_diff, &R));
+    return launch_blur_set(c, d_up, p.layer(0, 0), p.n_img, p.h[0], p.w[0], p.pitch[0], p.img_stride(0), R, 0,
+                           nullptr, 0, 0, 0, 0);
+}
+
+// second - first (sift_impl.py:109), float4 where possible
+__global__ void __launch_bounds__(256) dog_kernel(const float *__restrict__ a, const float *__restrict__ b,
+                                                  float *__restrict__ out, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * 256;
+    for (; i < n; i += stride) out[i] = __fsub_rn(b[i], a[i]);
+}
+
+int launch_dog(b200sift_ctx *c, const float *a, const float *b, float *out, size_t n)
+{
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > c->sm_count * 16) blocks = c->sm_count * 16;
+    if (blocks < 1) blocks = 1;
+    dog_kernel<<<blocks, 256, 0, c->stream>>>(a, b, out, n);
+    c->launches++;
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace b200
