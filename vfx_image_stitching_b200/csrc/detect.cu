@@ -341,18 +341,22 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
         const int h = v.h[o], w = v.w[o], pitch = v.pitch[o];
         const float *gimg = v.layer(o, layer, img);
         const float scale = (float)(dp.scale_factor * (double)L.size) / (float)(1 << (o + 1));
-        const int radius = (int)rintf(dp.radius_factor_f * scale);
+        const int radius = (int)fminf(rintf(dp.radius_factor_f * scale), 1048576.f);
         const float weight_fac = -0.5f / (scale * scale);
         const int cy = (int)rintf(L.y / (float)(1 << o));
         const int cx = (int)rintf(L.x / (float)(1 << o));
         for (int b = 0; b < nb; ++b) hist[b][lane] = 0.0;
-        const int side = 2 * radius + 1;
-        const int total = side * side;
+        // the window clipped to the pixels the reference does not skip (:262-264)
+        const int ylo = max(cy - radius, 1), yhi = min(cy + radius, h - 2);
+        const int xlo = max(cx - radius, 1), xhi = min(cx + radius, w - 2);
+        const int nx = xhi - xlo + 1, ny = yhi - ylo + 1;
+        const int total = (nx > 0 && ny > 0) ? nx * ny : 0;
+        int yy = lane / max(nx, 1), xx = lane - yy * max(nx, 1);
         for (int idx = lane; idx < total; idx += 32) {
-            const int r = idx / side;
-            const int dy = r - radius, dx = idx - r * side - radius;
-            const int y = cy + dy, x = cx + dx;
-            if (x <= 0 || x >= w - 1 || y <= 0 || y >= h - 1) continue;
+            const int y = ylo + yy, x = xlo + xx;
+            const int dy = y - cy, dx = x - cx;
+            xx += 32;
+            while (xx >= nx) { xx -= nx; ++yy; }
             const float *p = gimg + (size_t)y * pitch + x;
             const float gx = p[1] - p[-1];
             const float gy = p[-pitch] - p[pitch];
@@ -474,13 +478,17 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
         const float bins_per_deg = (float)(8 / 360.);
 
         for (int b = 0; b < 128; ++b) hist[b * 32 + lane] = 0.f;
-        const int side = 2 * half_w + 1;
-        const long long total = ok ? (long long)side * side : 0;
-        for (long long idx = lane; idx < total; idx += 32) {
-            const int r = (int)(idx / side);
-            const int ys = r - half_w, xs = (int)(idx - (long long)r * side) - half_w;
-            const int rr = pty + ys, cc = ptx + xs;
-            if (!(rr > 0 && rr < rows - 1 && cc > 0 && cc < cols - 1)) continue;
+        // the window clipped to the pixels that pass the first mask (:400)
+        const int rlo = max(pty - half_w, 1), rhi = min(pty + half_w, rows - 2);
+        const int clo = max(ptx - half_w, 1), chi = min(ptx + half_w, cols - 2);
+        const int nx = chi - clo + 1, ny = rhi - rlo + 1;
+        const int total = (ok && nx > 0 && ny > 0) ? nx * ny : 0;
+        int yy = lane / max(nx, 1), xx = lane - yy * max(nx, 1);
+        for (int idx = lane; idx < total; idx += 32) {
+            const int rr = rlo + yy, cc = clo + xx;
+            const int ys = rr - pty, xs = cc - ptx;
+            xx += 32;
+            while (xx >= nx) { xx -= nx; ++yy; }
             const double r_rot = xs * sin_a + ys * cos_a;
             const double c_rot = xs * cos_a - ys * sin_a;
             const double qr = r_rot / hw, qc = c_rot / hw;
