@@ -145,6 +145,20 @@ B200SIFT_API int b200sift_match(b200sift_ctx *ctx, const uint8_t *A, int nA, con
 B200SIFT_API int b200sift_match_images(b200sift_ctx *ctx, int imgA, int imgB, int desc_thresh, int32_t *ia,
                           int32_t *ib, float *xyxy, int32_t *n_matches);
 
+/* The first loop of run_panorama (image_stitching_sift.py:312-327) for n_pairs
+ * image pairs (pairs[2p] -> pairs[2p+1]) of the last detect_describe in ONE
+ * device pass: matcher (:63-73), acceptance best < desc_thresh (:74-79) and the
+ * ransac() vote (:86-111).  Per pair: shifts[2p..2p+1] = voted (dx,dy) ((0,0)
+ * without matches), n_matches[p], best_index[p] (-1 without matches) and
+ * best_xyxy[4p..] = the winning ((xA,yA),(xB,yB)).  Any output may be NULL. */
+B200SIFT_API int b200sift_match_pairs(b200sift_ctx *ctx, int n_pairs, const int32_t *pairs, int desc_thresh,
+                                      double dist_sq_thresh, double *shifts, int32_t *n_matches,
+                                      int32_t *best_index, float *best_xyxy);
+
+/* Match list of pair p of the last b200sift_match_pairs call (A order):
+ * ia / ib keypoint indices and xyxy (n x 4); capacity n_matches[p]. */
+B200SIFT_API int b200sift_get_pair_matches(b200sift_ctx *ctx, int p, int32_t *ia, int32_t *ib, float *xyxy);
+
 /* ransac() translation vote (image_stitching_sift.py:86-111) on the device:
  * matches n x 4 float (xA,yA,xB,yB); returns the winning index in *best
  * (first maximum; -1 when n == 0) and its (dx,dy) in move[2]. */

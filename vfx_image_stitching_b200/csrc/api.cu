@@ -147,7 +147,7 @@ void b200sift_destroy(b200sift_ctx *c)
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->pyr.base, c->d_up, c->d_in, c->d_dog, c->d_cand, c->d_loc, c->d_raw, c->d_raw_desc,
                     c->d_sort_idx, c->d_keep, c->d_pos, c->d_cub_tmp, c->d_kps, c->d_desc, c->d_counters,
-                    c->d_mA, c->d_mB, c->d_mout, c->d_nrmB, c->d_misc};
+                    c->d_mA, c->d_mB, c->d_mout, c->d_nrmB, c->d_misc, c->d_pair};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -383,6 +383,62 @@ int b200sift_match_images(b200sift_ctx *c, int imgA, int imgB, int desc_thresh, 
         B200_CUDA(cudaStreamSynchronize(c->stream));
     }
     *n_matches = n;
+    return 0;
+}
+
+int b200sift_match_pairs(b200sift_ctx *c, int n_pairs, const int32_t *pairs, int desc_thresh, double vote_thr,
+                         double *shifts, int32_t *n_matches, int32_t *best_index, float *best_xyxy)
+{
+    B200_ARG(c && n_pairs >= 0 && (n_pairs == 0 || pairs));
+    if (!c->have_results) {
+        set_error("match_pairs before a successful detect_describe");
+        return B200SIFT_ESTATE;
+    }
+    c->pair_n = 0;
+    if (n_pairs == 0) return 0;
+    B200_CUDA(cudaSetDevice(c->device));
+    std::vector<PairDesc> pd(n_pairs);
+    for (int p = 0; p < n_pairs; ++p) {
+        const int a = pairs[2 * p], b = pairs[2 * p + 1];
+        B200_ARG(a >= 0 && a < c->n_img_last && b >= 0 && b < c->n_img_last);
+        pd[p].offA = c->img_off[a];
+        pd[p].nA = c->img_off[a + 1] - c->img_off[a];
+        pd[p].offB = c->img_off[b];
+        pd[p].nB = c->img_off[b + 1] - c->img_off[b];
+    }
+    Timer tm(c);
+    B200_CHECK(run_match_pairs(c, n_pairs, pd.data(), desc_thresh, vote_thr));
+    std::vector<PairResult> res(n_pairs);
+    B200_CUDA(cudaMemcpyAsync(res.data(), c->d_pair_res, sizeof(PairResult) * n_pairs, cudaMemcpyDeviceToHost,
+                              c->stream));
+    tm.stop();
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    c->pair_counts.assign(n_pairs, 0);
+    for (int p = 0; p < n_pairs; ++p) {
+        c->pair_counts[p] = res[p].n_matches;
+        if (shifts) { shifts[2 * p] = res[p].dx; shifts[2 * p + 1] = res[p].dy; }
+        if (n_matches) n_matches[p] = res[p].n_matches;
+        if (best_index) best_index[p] = res[p].best;
+        if (best_xyxy) memcpy(best_xyxy + 4 * p, res[p].xyxy, sizeof(float) * 4);
+    }
+    return 0;
+}
+
+int b200sift_get_pair_matches(b200sift_ctx *c, int p, int32_t *ia, int32_t *ib, float *xyxy)
+{
+    B200_ARG(c != nullptr);
+    if (p < 0 || p >= c->pair_n || (int)c->pair_counts.size() != c->pair_n) {
+        set_error("get_pair_matches: pair %d is not part of the last match_pairs call", p);
+        return B200SIFT_ESTATE;
+    }
+    const int n = c->pair_counts[p];
+    if (n == 0) return 0;
+    const size_t mo = (size_t)p * c->pair_rows_max;
+    if (ia) B200_CUDA(cudaMemcpyAsync(ia, c->d_pair_ia + mo, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (ib) B200_CUDA(cudaMemcpyAsync(ib, c->d_pair_ib + mo, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    if (xyxy)
+        B200_CUDA(cudaMemcpyAsync(xyxy, c->d_pair_xy + 4 * mo, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

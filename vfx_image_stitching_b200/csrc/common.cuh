@@ -88,6 +88,10 @@ struct RawKeypoint {
     uint64_t order;  // (candidate scan order << 6) | peak bin
 };
 
+// one requested image pair of the batched matcher / its result
+struct PairDesc { int offA, nA, offB, nB; };
+struct PairResult { double dx, dy; int n_matches, best; float xyxy[4]; };
+
 struct DetectParams {
     int num_intervals, border, max_iter, ori_bins;
     float dog_thresh;       // floor(0.5*contrast/num_intervals*255)
@@ -138,6 +142,10 @@ struct b200sift_ctx {
     int32_t *d_mout = nullptr; size_t mout_cap = 0;
     int32_t *d_nrmB = nullptr; size_t nrmB_cap = 0;
     void *d_misc = nullptr; size_t misc_cap = 0;
+    uint8_t *d_pair = nullptr; size_t pair_cap = 0;   // batched pair matching scratch
+    b200::PairResult *d_pair_res = nullptr; int32_t *d_pair_ia = nullptr, *d_pair_ib = nullptr;
+    float *d_pair_xy = nullptr; int pair_rows_max = 0, pair_n = 0;
+    std::vector<int> pair_counts;
 };
 
 namespace b200 {
@@ -182,6 +190,7 @@ int launch_cyl(b200sift_ctx *c, const uint8_t *d_src, int h, int w, int ch, doub
 // match.cu
 int run_match(b200sift_ctx *c, const uint8_t *dA, int nA, const uint8_t *dB, int nB, int32_t *d_best_idx,
               int32_t *d_best_d2, int32_t *d_second_d2);
+int run_match_pairs(b200sift_ctx *c, int n_pairs, const PairDesc *h_pd, int thresh, double vote_thr);
 int run_accept(b200sift_ctx *c, const int32_t *d_idx, const int32_t *d_d2, int nA, int thresh,
                const b200sift_keypoint *kA, const b200sift_keypoint *kB, int32_t *d_ia, int32_t *d_ib,
                float *d_xyxy, int32_t *d_count);

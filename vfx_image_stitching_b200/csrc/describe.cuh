@@ -1,0 +1,220 @@
+// 4x4x8 SIFT descriptors, one warp per oriented keypoint (included by detect.cu, which is
+// compiled with --fmad=false).
+//
+// Replaces /root/reference/sift_impl.py:349-358 (unpack_octave) and :361-526
+// (generate_descriptors: window gather, trilinear scatter with np.add.at, threshold /
+// normalise / quantise).
+//
+// Two phases per 32 window pixels:
+//   filter  : every lane tests one pixel of the clipped (2*half_w+1)^2 window against the rotated
+//             4x4 grid (|r_rot|, |c_rot| < 2.5*hist_width, float32 with a safety margin -- half
+//             of the window fails, :429-430) and the survivors are compacted into a per-warp
+//             queue with a ballot;
+//   scatter : whenever 32 survivors are queued all lanes evaluate one each, with the reference's
+//             dtypes (float64 geometry :421-426, float32 gradient / orientation :414-417,:455-456),
+//             and add their 8 trilinear shares to a lane-private float32 4x4x8 histogram in
+//             shared memory ([bin][lane]: conflict free, no atomics).  Only the inner 4x4 cells
+//             of the reference's 6x6 tensor are ever read (:509), so shares of the border ring
+//             are dropped.
+// The 32 private histograms are then summed in a fixed order (deterministic), followed by the
+// 0.2 clip, renormalisation and round(512 v) of :512-524 with warp shuffles.
+#pragma once
+
+constexpr int kDescWarps = 4;
+constexpr int kDescHistFloats = 128 * 32;
+constexpr int kDescQueue = 96;
+constexpr size_t kDescSmemPerWarp = kDescHistFloats * sizeof(float) + 2 * kDescQueue * sizeof(int);
+
+__global__ void __launch_bounds__(kDescWarps * 32, 3)
+describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw, int n, int converted,
+                uint8_t *__restrict__ desc_out)
+{
+    extern __shared__ __align__(16) unsigned char dsm[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float *hist = reinterpret_cast<float *>(dsm + (size_t)wib * kDescSmemPerWarp);
+    int *qx = reinterpret_cast<int *>(hist + kDescHistFloats);
+    int *qy = qx + kDescQueue;
+    const int warps_total = gridDim.x * kDescWarps;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    for (int ki = blockIdx.x * kDescWarps + wib; ki < n; ki += warps_total) {
+        const RawKeypoint K = raw[ki];
+        // convert_keypoints_to_input_image_size (:333-343) unless already done
+        const float kx = converted ? K.x : K.x * 0.5f, ky = converted ? K.y : K.y * 0.5f;
+        const float ksize = converted ? K.size : K.size * 0.5f;
+        const int koct = converted ? K.octave_packed : ((K.octave_packed & ~255) | ((K.octave_packed - 1) & 255));
+        // unpack_octave (:349-358)
+        int octv = koct & 255;
+        const int lyr = (koct >> 8) & 255;
+        if (octv >= 128) octv |= -128;
+        const float scl = octv >= 0 ? 1.f / (float)(1 << octv) : (float)(1 << -octv);
+        const int po = octv + 1;
+        const bool ok = (po >= 0 && po < v.n_oct && lyr < v.n_layers);
+        const int rows = ok ? v.h[po] : 1, cols = ok ? v.w[po] : 1, pitch = ok ? v.pitch[po] : 1;
+        const float *img = ok ? v.layer(po, lyr, K.img) : nullptr;
+        const int ptx = (int)rint((double)scl * (double)kx);
+        const int pty = (int)rint((double)scl * (double)ky);
+        const double angle = 360. - (double)K.angle;
+        const double rad = angle * (3.14159265358979323846 / 180.0);
+        const double cos_a = cos(rad), sin_a = sin(rad);
+        const float hist_width = (float)dp.scale_multiplier_half * scl * ksize;
+        int half_w = (int)rint((double)hist_width * 1.4142135623730951 * 5 * 0.5);
+        const int diag = (int)sqrt((double)((long long)rows * rows + (long long)cols * cols));
+        half_w = min(half_w, diag);
+        const double hw = (double)hist_width;
+        const float anglef = (float)angle;
+        const float bins_per_deg = (float)(8 / 360.);
+        const float cos_f = (float)cos_a, sin_f = (float)sin_a;
+        const float lim = 2.5f * hist_width * 1.0001f + 1e-3f;  // float32 pre-filter, exact test below
+
+#pragma unroll 8
+        for (int b = 0; b < 128; ++b) hist[b * 32 + lane] = 0.f;
+
+        // Evaluate TWO surviving pixels per lane (window offsets xs, ys) and scatter their shares.
+        // Straight-line code on purpose: the two independent dependency chains (gather, sqrt,
+        // atan2, exp, shared-memory read-modify-write) interleave and hide each other's latency;
+        // with 16 KB of histogram per warp only 12 warps fit on an SM.
+        const double inv_hw = 1.0 / hw;
+        auto scatter2 = [&](const int (&xs)[2], const int (&ys)[2], const bool (&live)[2]) {
+            bool okc[2][4];
+            float *cell[2][4];
+            float mv[2][4], w0[2], w1[2];
+            int o0[2], o1[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const double r_rot = xs[u] * sin_a + ys[u] * cos_a;
+                const double c_rot = xs[u] * cos_a - ys[u] * sin_a;
+                const double qr = r_rot * inv_hw, qc = c_rot * inv_hw;
+                const double r_bin = qr + 1.5, c_bin = qc + 1.5;
+                const bool in = live[u] && (r_bin > -1.0 && r_bin < 4.0 && c_bin > -1.0 && c_bin < 4.0);
+                const float *p = img + (size_t)(pty + (in ? ys[u] : 0)) * pitch + (ptx + (in ? xs[u] : 0));
+                float gx = 0.f, gy = 0.f;
+                if (in) {
+                    gx = p[1] - p[-1];
+                    gy = p[-pitch] - p[pitch];
+                }
+                const float mag = sqrtf(gx * gx + gy * gy);
+                const float orient = mod360f(atan2f(gy, gx) * B200_RAD2DEGF);
+                const float fqr = (float)qr, fqc = (float)qc;
+                const float wm = expf(-0.125f * (fqr * fqr + fqc * fqc)) * mag;
+                float ob = (orient - anglef) * bins_per_deg;  // np.mod(ob, 8) in float32:
+                ob = ob - 8.f * truncf(ob * 0.125f);          // exact fmod for |ob| < 16
+                if (ob != 0.f) { if (ob < 0.f) ob += 8.f; } else ob = 0.f;
+                const int r0 = __double2int_rd(r_bin), c0 = __double2int_rd(c_bin);
+                o0[u] = ((int)floorf(ob)) & 7;
+                o1[u] = (o0[u] + 1) & 7;
+                const float rf = (float)(r_bin - (double)r0), cf = (float)(c_bin - (double)c0);
+                const float of = ob - (float)o0[u];
+                const float c1 = wm * rf, c0w = wm - c1;
+                mv[u][0] = c0w * (1.f - cf);  // (r0,   c0)
+                mv[u][1] = c0w * cf;          // (r0,   c0+1)
+                mv[u][2] = c1 * (1.f - cf);   // (r0+1, c0)
+                mv[u][3] = c1 * cf;           // (r0+1, c0+1)
+                w1[u] = of;
+                w0[u] = 1.f - of;
+                // inner cells only: tensor index r0+dr+1 in [1,4]  <=>  r0+dr in [0,3]
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int rb = r0 + (k >> 1), cb = c0 + (k & 1);
+                    okc[u][k] = in && ((unsigned)rb < 4u) && ((unsigned)cb < 4u);
+                    cell[u][k] = hist + ((rb * 4 + cb) * 8) * 32 + lane;
+                }
+            }
+            // The eight bins of one pixel are distinct: all loads before the first store.  The
+            // second pixel may hit the same bins, so it is applied after the first one's stores.
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                float h0[4], h1[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    h0[k] = okc[u][k] ? cell[u][k][o0[u] * 32] : 0.f;
+                    h1[k] = okc[u][k] ? cell[u][k][o1[u] * 32] : 0.f;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (okc[u][k]) {
+                        cell[u][k][o0[u] * 32] = h0[k] + mv[u][k] * w0[u];
+                        cell[u][k][o1[u] * 32] = h1[k] + mv[u][k] * w1[u];
+                    }
+                }
+            }
+        };
+
+        // the window clipped to the pixels that pass the first mask (:400)
+        const int rlo = max(pty - half_w, 1), rhi = min(pty + half_w, rows - 2);
+        const int clo = max(ptx - half_w, 1), chi = min(ptx + half_w, cols - 2);
+        const int nx = chi - clo + 1, ny = rhi - rlo + 1;
+        const int total = (ok && nx > 0 && ny > 0) ? nx * ny : 0;
+        int yy = lane / max(nx, 1), xx = lane - yy * max(nx, 1);
+        int qn = 0;  // warp-uniform queue length
+        for (int idx0 = 0; idx0 < total; idx0 += 32) {
+            const int ys = rlo + yy - pty, xs = clo + xx - ptx;
+            xx += 32;
+            while (xx >= nx) { xx -= nx; ++yy; }
+            const float fx = (float)xs, fy = (float)ys;
+            const bool keep = (idx0 + lane < total) && (fabsf(fx * sin_f + fy * cos_f) < lim) &&
+                              (fabsf(fx * cos_f - fy * sin_f) < lim);
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            if (keep) {
+                const int pos = qn + __popc(m & lt_mask);
+                qx[pos] = xs;
+                qy[pos] = ys;
+            }
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 64) {
+                const int sx[2] = {qx[lane], qx[lane + 32]}, sy[2] = {qy[lane], qy[lane + 32]};
+                const int tx = qx[lane + 64], ty = qy[lane + 64];
+                const bool live[2] = {true, true};
+                __syncwarp();
+                scatter2(sx, sy, live);
+                qn -= 64;
+                if (lane < qn) { qx[lane] = tx; qy[lane] = ty; }
+                __syncwarp();
+            }
+        }
+        if (qn > 0) {
+            const int sx[2] = {qx[lane], qx[lane + 32]}, sy[2] = {qy[lane], qy[lane + 32]};
+            const bool live[2] = {lane < qn, lane + 32 < qn};
+            scatter2(sx, sy, live);
+        }
+        __syncwarp();
+
+        float vq[4];
+        double ss = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = lane + 32 * q;
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // fixed order, 4 chains
+#pragma unroll
+            for (int l = 0; l < 32; l += 4) {
+                s0 += hist[e * 32 + ((l + lane) & 31)];
+                s1 += hist[e * 32 + ((l + 1 + lane) & 31)];
+                s2 += hist[e * 32 + ((l + 2 + lane) & 31)];
+                s3 += hist[e * 32 + ((l + 3 + lane) & 31)];
+            }
+            const float s = (s0 + s1) + (s2 + s3);
+            vq[q] = s;
+            ss += (double)(s * s);
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, sft);
+        const float thr = sqrtf((float)ss) * dp.descriptor_max_value_f;
+        double ss2 = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (vq[q] > thr) vq[q] = thr;
+            ss2 += (double)(vq[q] * vq[q]);
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) ss2 += __shfl_xor_sync(0xffffffffu, ss2, sft);
+        float norm_v = sqrtf((float)ss2);
+        if (norm_v < 1e-7f) norm_v = 1e-7f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float t = rintf(512.f * (vq[q] / norm_v));
+            t = fminf(fmaxf(t, 0.f), 255.f);
+            desc_out[(size_t)ki * 128 + lane + 32 * q] = (uint8_t)t;
+        }
+        __syncwarp();
+    }
+}

@@ -145,6 +145,95 @@ extrema_kernel(PyrView v, int o, int border, int num_intervals, float thresh, Ca
 }
 
 // ---------------------------------------------------------------------------
+// Register-sliding form of the same scan (used for the reference's
+// num_intervals = 3): no shared memory.  A warp owns 30 output columns (+1
+// halo lane each side) and marches down a segment of rows; per row every lane
+// loads its pixel of the NI+3 Gaussian layers (coalesced 128 B per layer),
+// forms the NI+2 DoG values in registers, gets the left / right neighbours by
+// warp shuffle and keeps the horizontal 3-max / 3-min of the last three rows.
+// "val >= all 26 neighbours" (ties pass, :151-156) is then
+//   val >= max3x3(layer-1) && val >= max3x3(layer) && val >= max3x3(layer+1)
+// (the centre is part of max3x3(layer), so that term is an equality test), and
+// likewise with min for negative values.  Each Gaussian value is read once
+// from HBM (24 B per pixel for 6 layers, + halo rows / lanes from L2).
+// ---------------------------------------------------------------------------
+constexpr int kExSegRows = 32;
+
+template <int NI>
+__global__ void __launch_bounds__(256)
+extrema_rows_kernel(PyrView v, int o, int border, float thresh, int n_cg, int n_rs, Candidate *__restrict__ cand,
+                    int cand_cap, int32_t *__restrict__ counters)
+{
+    constexpr int ND = NI + 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int img = blockIdx.y;
+    const int item = blockIdx.x * 8 + warp;
+    if (item >= n_cg * n_rs) return;  // whole warp
+    const int cg = item % n_cg, rs = item / n_cg;
+    const int h = v.h[o], w = v.w[o], pitch = v.pitch[o];
+    const size_t lstride = (size_t)v.n_img * h * pitch;
+    const float *g0 = v.layer(o, 0, img);
+    const int x = border + 30 * cg - 1 + lane;
+    const int xc = min(x, w - 1);
+    const bool out_lane = (lane >= 1) && (lane <= 30) && (x < w - border);
+    const int ybeg = border + rs * kExSegRows, yend = min(ybeg + kExSegRows, h - border);
+    float hmx[ND][3], hmn[ND][3], dprev[NI], dcur[NI];
+#pragma unroll
+    for (int l = 0; l < ND; ++l)
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { hmx[l][r] = 0.f; hmn[l][r] = 0.f; }
+#pragma unroll
+    for (int l = 0; l < NI; ++l) { dprev[l] = 0.f; dcur[l] = 0.f; }
+    for (int y = ybeg - 1; y <= yend; ++y) {
+        const float *p = g0 + (size_t)y * pitch + xc;
+        float g[ND + 1];
+#pragma unroll
+        for (int l = 0; l <= ND; ++l) g[l] = p[l * lstride];
+#pragma unroll
+        for (int l = 0; l < ND; ++l) {
+            const float d = __fsub_rn(g[l + 1], g[l]);
+            const float lf = __shfl_up_sync(0xffffffffu, d, 1), rt = __shfl_down_sync(0xffffffffu, d, 1);
+            hmx[l][0] = hmx[l][1]; hmx[l][1] = hmx[l][2]; hmx[l][2] = fmaxf(fmaxf(lf, d), rt);
+            hmn[l][0] = hmn[l][1]; hmn[l][1] = hmn[l][2]; hmn[l][2] = fminf(fminf(lf, d), rt);
+            if (l >= 1 && l <= NI) { dprev[l - 1] = dcur[l - 1]; dcur[l - 1] = d; }
+        }
+        if (y < ybeg + 1) continue;
+        float M[ND], m[ND];
+#pragma unroll
+        for (int l = 0; l < ND; ++l) {
+            M[l] = fmaxf(fmaxf(hmx[l][0], hmx[l][1]), hmx[l][2]);
+            m[l] = fminf(fminf(hmn[l][0], hmn[l][1]), hmn[l][2]);
+        }
+#pragma unroll
+        for (int li = 0; li < NI; ++li) {
+            const int l = li + 1;
+            const float val = dprev[li];
+            const bool ext = out_lane && ((val > thresh && val >= M[l - 1] && val >= M[l] && val >= M[l + 1]) ||
+                                          (val < -thresh && val <= m[l - 1] && val <= m[l] && val <= m[l + 1]));
+            const unsigned mk = __ballot_sync(0xffffffffu, ext);
+            if (mk) {
+                int base = 0;
+                const int leader = __ffs(mk) - 1;
+                if (lane == leader) {
+                    base = atomicAdd(&counters[CNT_CAND], __popc(mk));
+                    atomicAdd(&counters[CNT_HDR + img * CNT_PER_IMG + 0], __popc(mk));
+                }
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (ext) {
+                    const int idx = base + __popc(mk & ((1u << lane) - 1u));
+                    if (idx < cand_cap) {
+                        Candidate cd;
+                        cd.img_o_l = ((uint32_t)img << 16) | ((uint32_t)o << 8) | (uint32_t)l;
+                        cd.yx = ((uint32_t)(y - 1) << 16) | (uint32_t)x;
+                        cand[idx] = cd;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // quadratic-fit refinement (sift_impl.py:169-240), one thread per candidate
 // ---------------------------------------------------------------------------
 
@@ -206,6 +295,27 @@ __device__ void sym3_pinv_solve(const double H[3][3], const double g[3], double 
     }
 }
 
+// Fast path of the same solve: H is practically always well conditioned (smallest
+// singular-value ratio seen on the reference's sets: 6e-5), where the minimum-norm solution is
+// the ordinary one.  Adjugate / determinant in float64 (relative error ~cond*1e-16, invisible
+// after the cast to float32); anything close to singular takes the Jacobi pseudo-inverse above.
+__device__ __forceinline__ void sym3_solve(const double H[3][3], const double g[3], double x[3])
+{
+    const double a = H[0][0], b = H[0][1], c = H[0][2], d = H[1][1], e = H[1][2], f = H[2][2];
+    const double A = d * f - e * e, B = c * e - b * f, C = b * e - c * d;
+    const double det = a * A + b * B + c * C;
+    const double m = fmax(fmax(fabs(a), fabs(d)), fmax(fabs(f), fmax(fabs(b), fmax(fabs(c), fabs(e)))));
+    if (!(fabs(det) > 1e-9 * m * m * m)) {
+        sym3_pinv_solve(H, g, x);
+        return;
+    }
+    const double D = a * f - c * c, E = b * c - a * e, F = a * d - b * b;
+    const double inv = 1.0 / det;
+    x[0] = (A * g[0] + B * g[1] + C * g[2]) * inv;
+    x[1] = (B * g[0] + D * g[1] + E * g[2]) * inv;
+    x[2] = (C * g[0] + E * g[1] + F * g[2]) * inv;
+}
+
 __global__ void __launch_bounds__(128)
 refine_kernel(PyrView v, DetectParams dp, const Candidate *__restrict__ cand, int cand_cap,
               Localized *__restrict__ loc, int loc_cap, int32_t *__restrict__ counters)
@@ -255,7 +365,7 @@ refine_kernel(PyrView v, DetectParams dp, const Candidate *__restrict__ cand, in
 #pragma unroll
                 for (int j = 0; j < 3; ++j) Hd[i][j] = hess[i][j];
             }
-            sym3_pinv_solve(Hd, gd, xd);
+            sym3_solve(Hd, gd, xd);
 #pragma unroll
             for (int i = 0; i < 3; ++i) upd[i] = -(float)xd[i];
             if (fabsf(upd[0]) < 0.5f && fabsf(upd[1]) < 0.5f && fabsf(upd[2]) < 0.5f) break;
@@ -430,133 +540,7 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
     }
 }
 
-// ---------------------------------------------------------------------------
-// descriptors (sift_impl.py:349-526), one warp per oriented keypoint.
-// Window pixels are spread over the lanes; each lane scatters its trilinear
-// shares into a private float32 4x4x8 histogram ([bin][lane] in shared
-// memory -- only the inner 4x4 cells of the reference's 6x6 tensor are ever
-// read, :509), the 32 partial histograms are summed in a fixed order, then
-// threshold / normalise / quantise (:512-524) with warp shuffles.
-// ---------------------------------------------------------------------------
-constexpr int kDescWarps = 4;
-
-__global__ void __launch_bounds__(kDescWarps * 32)
-describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw, int n, int converted,
-                uint8_t *__restrict__ desc_out)
-{
-    extern __shared__ float dh_s[];  // [kDescWarps][128][32]
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    float *hist = dh_s + (size_t)wib * 128 * 32;
-    const int warps_total = gridDim.x * kDescWarps;
-    for (int ki = blockIdx.x * kDescWarps + wib; ki < n; ki += warps_total) {
-        const RawKeypoint K = raw[ki];
-        // convert_keypoints_to_input_image_size (:333-343) unless already done
-        const float kx = converted ? K.x : K.x * 0.5f, ky = converted ? K.y : K.y * 0.5f;
-        const float ksize = converted ? K.size : K.size * 0.5f;
-        const int koct = converted ? K.octave_packed
-                                   : ((K.octave_packed & ~255) | ((K.octave_packed - 1) & 255));
-        // unpack_octave (:349-358)
-        int octv = koct & 255;
-        const int lyr = (koct >> 8) & 255;
-        if (octv >= 128) octv |= -128;
-        const float scl = octv >= 0 ? 1.f / (float)(1 << octv) : (float)(1 << -octv);
-        const int po = octv + 1;
-        bool ok = (po >= 0 && po < v.n_oct && lyr < v.n_layers);
-        const int rows = ok ? v.h[po] : 1, cols = ok ? v.w[po] : 1, pitch = ok ? v.pitch[po] : 1;
-        const float *img = ok ? v.layer(po, lyr, K.img) : nullptr;
-        const int ptx = (int)rint((double)scl * (double)kx);
-        const int pty = (int)rint((double)scl * (double)ky);
-        const double angle = 360. - (double)K.angle;
-        const double rad = angle * (3.14159265358979323846 / 180.0);
-        const double cos_a = cos(rad), sin_a = sin(rad);
-        const float hist_width = (float)dp.scale_multiplier_half * scl * ksize;
-        int half_w = (int)rint((double)hist_width * 1.4142135623730951 * 5 * 0.5);
-        const int diag = (int)sqrt((double)((long long)rows * rows + (long long)cols * cols));
-        half_w = min(half_w, diag);
-        const double hw = (double)hist_width;
-        const float anglef = (float)angle;
-        const float bins_per_deg = (float)(8 / 360.);
-
-        for (int b = 0; b < 128; ++b) hist[b * 32 + lane] = 0.f;
-        // the window clipped to the pixels that pass the first mask (:400)
-        const int rlo = max(pty - half_w, 1), rhi = min(pty + half_w, rows - 2);
-        const int clo = max(ptx - half_w, 1), chi = min(ptx + half_w, cols - 2);
-        const int nx = chi - clo + 1, ny = rhi - rlo + 1;
-        const int total = (ok && nx > 0 && ny > 0) ? nx * ny : 0;
-        int yy = lane / max(nx, 1), xx = lane - yy * max(nx, 1);
-        for (int idx = lane; idx < total; idx += 32) {
-            const int rr = rlo + yy, cc = clo + xx;
-            const int ys = rr - pty, xs = cc - ptx;
-            xx += 32;
-            while (xx >= nx) { xx -= nx; ++yy; }
-            const double r_rot = xs * sin_a + ys * cos_a;
-            const double c_rot = xs * cos_a - ys * sin_a;
-            const double qr = r_rot / hw, qc = c_rot / hw;
-            const double r_bin = qr + 2.0 - 0.5;
-            const double c_bin = qc + 2.0 - 0.5;
-            if (!(r_bin > -1.0 && r_bin < 4.0 && c_bin > -1.0 && c_bin < 4.0)) continue;
-            const float *p = img + (size_t)rr * pitch + cc;
-            const float gx = p[1] - p[-1];
-            const float gy = p[-pitch] - p[pitch];
-            const float mag = sqrtf(gx * gx + gy * gy);
-            const float orient = mod360f(atan2f(gy, gx) * B200_RAD2DEGF);
-            const double wgt = exp(-0.125 * (qr * qr + qc * qc));
-            const double wmag = wgt * (double)mag;
-            float ob = fmodf((orient - anglef) * bins_per_deg, 8.f);  // np.mod(ob, 8) in float32
-            if (ob != 0.f) { if (ob < 0.f) ob += 8.f; } else ob = 0.f;
-            const int r0 = (int)floor(r_bin), c0 = (int)floor(c_bin);
-            int o0 = (int)floorf(ob);
-            o0 = ((o0 % 8) + 8) % 8;
-            const double rf = r_bin - (double)r0, cf = c_bin - (double)c0, of = (double)ob - (double)o0;
-            const double c1 = wmag * rf, c0w = wmag - c1;
-            const double c10 = c1 * (1 - cf), c11 = c1 * cf, c00 = c0w * (1 - cf), c01 = c0w * cf;
-            const int o1 = (o0 + 1) & 7;
-            // inner cells only: tensor index r0+dr+1 in [1,4]  <=>  r0+dr in [0,3]
-#define B200_SCATTER(RB, CB, M)                                              \
-    if ((unsigned)(RB) < 4u && (unsigned)(CB) < 4u) {                        \
-        float *cell = hist + (((RB) * 4 + (CB)) * 8) * 32 + lane;            \
-        cell[o0 * 32] += (float)((M) * (1 - of));                            \
-        cell[o1 * 32] += (float)((M) * of);                                  \
-    }
-            B200_SCATTER(r0, c0, c00)
-            B200_SCATTER(r0, c0 + 1, c01)
-            B200_SCATTER(r0 + 1, c0, c10)
-            B200_SCATTER(r0 + 1, c0 + 1, c11)
-#undef B200_SCATTER
-        }
-        __syncwarp();
-        float vq[4];
-        double ss = 0.0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const int e = lane + 32 * q;
-            float s = 0.f;
-            for (int l = 0; l < 32; ++l) s += hist[e * 32 + ((l + lane) & 31)];
-            vq[q] = s;
-            ss += (double)(s * s);
-        }
-#pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, sft);
-        const float thr = sqrtf((float)ss) * dp.descriptor_max_value_f;
-        double ss2 = 0.0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (vq[q] > thr) vq[q] = thr;
-            ss2 += (double)(vq[q] * vq[q]);
-        }
-#pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) ss2 += __shfl_xor_sync(0xffffffffu, ss2, sft);
-        float norm_v = sqrtf((float)ss2);
-        if (norm_v < 1e-7f) norm_v = 1e-7f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float t = rintf(512.f * (vq[q] / norm_v));
-            t = fminf(fmaxf(t, 0.f), 255.f);
-            desc_out[(size_t)ki * 128 + lane + 32 * q] = (uint8_t)t;
-        }
-        __syncwarp();
-    }
-}
+#include "describe.cuh"
 
 // ---------------------------------------------------------------------------
 // ordering + de-duplication (sift_impl.py:299-327) + conversion (:333-343)
@@ -704,9 +688,17 @@ int run_detect(b200sift_ctx *c, const b200sift_params &p, int /*want_scan_order*
         for (int o = 0; o < py.n_oct; ++o) {
             const int sh = py.h[o] - 2 * p.image_border_width, sw = py.w[o] - 2 * p.image_border_width;
             if (sh <= 0 || sw <= 0) continue;
-            dim3 grid((sw + kExTW - 1) / kExTW, (sh + kExTH - 1) / kExTH, py.n_img);
-            extrema_kernel<<<grid, 256, ex_smem, c->stream>>>(v, o, p.image_border_width, p.num_intervals,
-                                                              dp.dog_thresh, c->d_cand, c->cand_cap, c->d_counters);
+            if (p.num_intervals == 3 && sw >= 24) {
+                const int n_cg = (sw + 29) / 30, n_rs = (sh + kExSegRows - 1) / kExSegRows;
+                dim3 grid((n_cg * n_rs + 7) / 8, py.n_img);
+                extrema_rows_kernel<3><<<grid, 256, 0, c->stream>>>(v, o, p.image_border_width, dp.dog_thresh, n_cg,
+                                                                   n_rs, c->d_cand, c->cand_cap, c->d_counters);
+            } else {
+                dim3 grid((sw + kExTW - 1) / kExTW, (sh + kExTH - 1) / kExTH, py.n_img);
+                extrema_kernel<<<grid, 256, ex_smem, c->stream>>>(v, o, p.image_border_width, p.num_intervals,
+                                                                  dp.dog_thresh, c->d_cand, c->cand_cap,
+                                                                  c->d_counters);
+            }
             c->launches++;
         }
         B200_CUDA(cudaGetLastError());
@@ -744,7 +736,7 @@ int run_describe(b200sift_ctx *c, const b200sift_params &p, const RawKeypoint *d
     B200_ARG(p.window_width == 4 && p.desc_bins == 8);
     const PyrView v = make_view(c->pyr);
     const DetectParams dp = make_detect_params(p);
-    const size_t smem = (size_t)kDescWarps * 128 * 32 * sizeof(float);
+    const size_t smem = (size_t)kDescWarps * kDescSmemPerWarp;
     static bool attr = false;
     if (!attr) {
         B200_CUDA(cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

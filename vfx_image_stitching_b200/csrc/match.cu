@@ -132,6 +132,206 @@ int run_match(b200sift_ctx *c, const uint8_t *dA, int nA, const uint8_t *dB, int
     return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Batched form: every requested pair of the last detect in one pass
+// (image_stitching_sift.py:312-327 runs compute_shift_sift per adjacent pair).
+//   match_pairs_kernel   grid (row tiles, B chunks, pairs): per-chunk top-2
+//   pair_finalize_kernel one CTA per pair: merge the chunks, accept best < thresh
+//                        (:74), compact in A order (block scan), then the ransac()
+//                        vote (:86-111, float64, first maximum wins).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMatchRows)
+match_pairs_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ nrm,
+                   const PairDesc *__restrict__ pd, int n_chunks_max, int rows_max,
+                   int32_t *__restrict__ part /*[pair][rows_max][n_chunks_max][3]*/)
+{
+    __shared__ uint4 b_s[kMatchTile * 8];
+    __shared__ int32_t nb_s[kMatchTile];
+    const PairDesc P = pd[blockIdx.z];
+    const int chunk = blockIdx.y;
+    if ((int)(blockIdx.x * kMatchRows) >= P.nA) return;
+    const int j_begin = chunk * kMatchChunk, j_end = min(P.nB, j_begin + kMatchChunk);
+    if (j_begin >= P.nB && chunk > 0) return;
+    const uint8_t *A = desc + (size_t)P.offA * 128, *B = desc + (size_t)P.offB * 128;
+    const int32_t *nrmB = nrm + P.offB;
+    const int i = blockIdx.x * kMatchRows + threadIdx.x;
+    uint32_t a[32];
+    unsigned na = 0;
+    {
+        const int ii = min(i, P.nA - 1);
+        const uint4 *p = reinterpret_cast<const uint4 *>(A + (size_t)ii * 128);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const uint4 v = p[q];
+            a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) na = __dp4a(a[q], a[q], na);
+    }
+    int b1 = INT_MAX, b2 = INT_MAX, bi = -1;
+    for (int j0 = j_begin; j0 < j_end; j0 += kMatchTile) {
+        const int nt = min(kMatchTile, j_end - j0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nt * 8; t += kMatchRows)
+            b_s[t] = reinterpret_cast<const uint4 *>(B + (size_t)j0 * 128)[t];
+        for (int t = threadIdx.x; t < nt; t += kMatchRows) nb_s[t] = nrmB[j0 + t];
+        __syncthreads();
+        for (int t = 0; t < nt; ++t) {
+            unsigned dot = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const uint4 v = b_s[t * 8 + q];
+                dot = __dp4a(a[4 * q], v.x, dot);
+                dot = __dp4a(a[4 * q + 1], v.y, dot);
+                dot = __dp4a(a[4 * q + 2], v.z, dot);
+                dot = __dp4a(a[4 * q + 3], v.w, dot);
+            }
+            const int d = (int)na + nb_s[t] - 2 * (int)dot;
+            if (d < b1) { b2 = b1; b1 = d; bi = j0 + t; }
+            else if (d < b2) b2 = d;
+        }
+    }
+    if (i < P.nA) {
+        int32_t *o = part + (((size_t)blockIdx.z * rows_max + i) * n_chunks_max + chunk) * 3;
+        o[0] = bi; o[1] = b1; o[2] = b2;
+    }
+}
+
+constexpr int kFinThreads = 1024;
+
+__global__ void __launch_bounds__(kFinThreads)
+pair_finalize_kernel(const PairDesc *__restrict__ pd, const int32_t *__restrict__ part, int n_chunks_max,
+                     int rows_max, const b200sift_keypoint *__restrict__ kps, int thresh, double vote_thr,
+                     int32_t *__restrict__ m_ia, int32_t *__restrict__ m_ib, float *__restrict__ m_xy,
+                     double *__restrict__ m_mv, PairResult *__restrict__ res)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    __shared__ unsigned long long s_red[32];
+    const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const PairDesc P = pd[pair];
+    const int nck = P.nB > 0 ? (P.nB + kMatchChunk - 1) / kMatchChunk : 1;
+    const b200sift_keypoint *kA = kps + P.offA, *kB = kps + P.offB;
+    const size_t mo = (size_t)pair * rows_max;
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+    for (int row0 = 0; row0 < P.nA; row0 += kFinThreads) {
+        const int i = row0 + tid;
+        int b1 = INT_MAX, bi = -1;
+        if (i < P.nA) {
+            const int32_t *o = part + ((size_t)pair * rows_max + i) * n_chunks_max * 3;
+            for (int c = 0; c < nck; ++c) {
+                const int ci = o[3 * c], c1 = o[3 * c + 1];
+                if (ci >= 0 && c1 < b1) { b1 = c1; bi = ci; }   // strict <: the earlier chunk (lower j) wins ties
+            }
+        }
+        const bool keep = (bi != -1) && (b1 < thresh);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = s_base, total = 0;
+        for (int w2 = 0; w2 < kFinThreads / 32; ++w2) {
+            const int c = s_warp[w2];
+            if (w2 < warp) before += c;
+            total += c;
+        }
+        if (keep) {
+            const int d = before + __popc(m & ((1u << lane) - 1u));
+            m_ia[mo + d] = i;
+            m_ib[mo + d] = bi;
+            const float xa = kA[i].x, ya = kA[i].y, xb = kB[bi].x, yb = kB[bi].y;
+            m_xy[4 * (mo + d)] = xa; m_xy[4 * (mo + d) + 1] = ya; m_xy[4 * (mo + d) + 2] = xb; m_xy[4 * (mo + d) + 3] = yb;
+            m_mv[2 * (mo + d)] = (double)xa - (double)xb;       // :94-96 python floats
+            m_mv[2 * (mo + d) + 1] = (double)ya - (double)yb;
+        }
+        __syncthreads();
+        if (tid == 0) s_base += total;
+        __syncthreads();
+    }
+    const int n = s_base;
+    unsigned long long key = 0;
+    for (int i = tid; i < n; i += kFinThreads) {
+        const double dxr = m_mv[2 * (mo + i)], dyr = m_mv[2 * (mo + i) + 1];
+        unsigned votes = 0;
+        for (int j = 0; j < n; ++j) {
+            const double dx = m_mv[2 * (mo + j)] - dxr, dy = m_mv[2 * (mo + j) + 1] - dyr;
+            votes += (dx * dx + dy * dy < vote_thr) ? 1u : 0u;
+        }
+        const unsigned long long k = ((unsigned long long)votes << 32) | (unsigned)(~(unsigned)i);
+        if (k > key) key = k;
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        const unsigned long long o = __shfl_xor_sync(0xffffffffu, key, sft);
+        if (o > key) key = o;
+    }
+    if (lane == 0) s_red[warp] = key;
+    __syncthreads();
+    if (tid == 0) {
+        for (int w2 = 1; w2 < kFinThreads / 32; ++w2)
+            if (s_red[w2] > key) key = s_red[w2];
+        PairResult r;
+        r.n_matches = n;
+        if (n > 0) {
+            const int best = (int)(~(unsigned)(key & 0xffffffffu));
+            r.best = best;
+            r.dx = m_mv[2 * (mo + best)];
+            r.dy = m_mv[2 * (mo + best) + 1];
+            for (int k2 = 0; k2 < 4; ++k2) r.xyxy[k2] = m_xy[4 * (mo + best) + k2];
+        } else {
+            r.best = -1;
+            r.dx = r.dy = 0;
+            for (int k2 = 0; k2 < 4; ++k2) r.xyxy[k2] = 0.f;
+        }
+        res[pair] = r;
+    }
+}
+
+// norms of all final descriptors + both kernels above; results land in c->d_pair_res.
+int run_match_pairs(b200sift_ctx *c, int n_pairs, const PairDesc *h_pd, int thresh, double vote_thr)
+{
+    int rows_max = 1, nb_max = 1, n_total = c->img_off.empty() ? 0 : c->img_off.back();
+    for (int p = 0; p < n_pairs; ++p) {
+        rows_max = h_pd[p].nA > rows_max ? h_pd[p].nA : rows_max;
+        nb_max = h_pd[p].nB > nb_max ? h_pd[p].nB : nb_max;
+    }
+    const int n_chunks = (nb_max + kMatchChunk - 1) / kMatchChunk;
+    size_t cap = c->nrmB_cap;
+    B200_CHECK(ensure(&c->d_nrmB, &cap, (size_t)(n_total > 0 ? n_total : 1)));
+    c->nrmB_cap = cap;
+    cap = c->mout_cap;
+    B200_CHECK(ensure(&c->d_mout, &cap, (size_t)n_pairs * rows_max * n_chunks * 3));
+    c->mout_cap = cap;
+    // per-pair scratch: pd | res | ia | ib | xy | mv
+    const size_t rows = (size_t)n_pairs * rows_max;
+    const size_t bytes = (size_t)n_pairs * (sizeof(PairDesc) + sizeof(PairResult)) + rows * (4 + 4 + 16 + 16) + 256;
+    cap = c->pair_cap;
+    B200_CHECK(ensure(&c->d_pair, &cap, bytes));
+    c->pair_cap = cap;
+    uint8_t *base = c->d_pair;
+    double *m_mv = (double *)base;                     base += rows * 16;
+    PairResult *res = (PairResult *)base;              base += (size_t)n_pairs * sizeof(PairResult);
+    float *m_xy = (float *)base;                       base += rows * 16;
+    PairDesc *pd = (PairDesc *)base;                   base += (size_t)n_pairs * sizeof(PairDesc);
+    int32_t *m_ia = (int32_t *)base;                   base += rows * 4;
+    int32_t *m_ib = (int32_t *)base;
+    c->pair_rows_max = rows_max;
+    c->pair_n = n_pairs;
+    c->d_pair_res = res; c->d_pair_ia = m_ia; c->d_pair_ib = m_ib; c->d_pair_xy = m_xy;
+    B200_CUDA(cudaMemcpyAsync(pd, h_pd, sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, c->stream));
+    if (n_total > 0) {
+        norms_kernel<<<(n_total + 255) / 256, 256, 0, c->stream>>>(c->d_desc, n_total, c->d_nrmB);
+        c->launches++;
+    }
+    dim3 grid((rows_max + kMatchRows - 1) / kMatchRows, n_chunks, n_pairs);
+    match_pairs_kernel<<<grid, kMatchRows, 0, c->stream>>>(c->d_desc, c->d_nrmB, pd, n_chunks, rows_max, c->d_mout);
+    pair_finalize_kernel<<<n_pairs, kFinThreads, 0, c->stream>>>(pd, c->d_mout, n_chunks, rows_max, c->d_kps, thresh,
+                                                                vote_thr, m_ia, m_ib, m_xy, m_mv, res);
+    c->launches += 2;
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // accepted matches of image_stitching_sift.py:74-79, compacted in A order
 __global__ void __launch_bounds__(256)
 accept_flag_kernel(const int32_t *__restrict__ best_idx, const int32_t *__restrict__ best_d2, int nA, int thresh,

@@ -7,6 +7,7 @@
 // :82-97 generate_gaussian_images (incremental cv2.GaussianBlur chain +
 // INTER_NEAREST decimation), :100-111 generate_DoG_images.
 #include <math.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace b200 {
@@ -19,6 +20,7 @@ struct TapCache {
     double sigma[16];
     int radius[16];
     bool valid[16];
+    float taps[16][kMaxBlurRadius + 1];  // host copy: the strip kernel takes its taps as a parameter
 };
 static TapCache g_taps[16];  // per device ordinal
 
@@ -58,6 +60,7 @@ static int upload_taps(b200sift_ctx *c, int set, double sigma, int *radius)
     B200_CUDA(cudaStreamSynchronize(c->stream));
     B200_CUDA(cudaMemcpyToSymbol(c_taps, taps, sizeof(taps), (size_t)set * sizeof(taps)));
     tc.valid[set] = true;
+    memcpy(tc.taps[set], taps, sizeof(taps));
     tc.sigma[set] = sigma;
     tc.radius[set] = r;
     *radius = r;
@@ -130,151 +133,7 @@ int launch_gray_upsample(b200sift_ctx *c, const void *d_in, size_t img_stride_by
     return 0;
 }
 
-// ---------------------------------------------------------------------------
-// Separable Gaussian blur, strip kernel.
-//
-// One CTA owns a 256-column strip of `seg_rows` output rows of one image and
-// marches down it in batches of 8 rows:
-//   global -> (register prefetch) -> in_s[8][256+2RP]      raw rows + x halo
-//   row pass, 4 adjacent outputs per thread from float4 LDS -> ring[2R+8][256]
-//   column pass, one column x 8 rows per thread from the ring -> global
-// Every input float is read once from HBM (+ 2RP/256 halo from L2, + 2R/seg
-// rows of y halo) and every output written once: 8 B per pixel.  The optional
-// dst2 receives the [::2, ::2] decimation that seeds the next octave
-// (sift_impl.py:95-96), saving a separate pass.
-// Arithmetic: k0*c + sum_k k[k]*(a[+k] + a[-k]) in float32 (fmaf), rows then
-// columns, BORDER_REFLECT_101 -- the structure of OpenCV's symmetric
-// separable float filter.
-// ---------------------------------------------------------------------------
-constexpr int kStripW = 256;
-constexpr int kStripBR = 8;
-
-template <int R>
-__global__ void __launch_bounds__(256, 2)
-blur_strip_kernel(const float *__restrict__ src, float *__restrict__ dst, float *__restrict__ dst2, int h, int w,
-                  int pitch, size_t img_stride, int h2, int w2, int pitch2, size_t img_stride2, int seg_rows,
-                  int tapset)
-{
-    constexpr int TW = kStripW, BR = kStripBR;
-    constexpr int RP = (R + 3) & ~3;
-    constexpr int INW = TW + 2 * RP;
-    constexpr int RING = 2 * R + BR;
-    constexpr int NV4 = BR * INW / 4;            // float4 slots of one input batch
-    constexpr int NV = (NV4 + 255) / 256;        // per thread
-    extern __shared__ __align__(16) float smem[];
-    float *in_s = smem;                // [BR][INW]
-    float *ring = smem + BR * INW;     // [RING][TW]
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x0 = blockIdx.x * TW;
-    const int ys = blockIdx.y * seg_rows;
-    const int ye = min(ys + seg_rows, h);
-    src += (size_t)blockIdx.z * img_stride;
-    dst += (size_t)blockIdx.z * img_stride;
-    if (dst2) dst2 += (size_t)blockIdx.z * img_stride2;
-
-    float taps[R + 1];
-#pragma unroll
-    for (int k = 0; k <= R; ++k) taps[k] = c_taps[tapset][k];
-
-    float4 pre[NV];
-    auto gload = [&](int yb) {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int f = tid + i * 256;
-            if (f < NV4) {
-                const int row = f / (INW / 4), c4 = f - row * (INW / 4);
-                const int y = reflect101(yb + row, h);
-                const int x = x0 - RP + 4 * c4;
-                const float *p = src + (size_t)y * pitch;
-                if (x >= 0 && x + 3 < w) {
-                    pre[i] = *reinterpret_cast<const float4 *>(p + x);
-                } else {
-                    pre[i].x = p[reflect101(x, w)];
-                    pre[i].y = p[reflect101(x + 1, w)];
-                    pre[i].z = p[reflect101(x + 2, w)];
-                    pre[i].w = p[reflect101(x + 3, w)];
-                }
-            }
-        }
-    };
-    auto sstore = [&]() {
-#pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int f = tid + i * 256;
-            if (f < NV4) reinterpret_cast<float4 *>(in_s)[f] = pre[i];
-        }
-    };
-
-    const int n_batches = (ye - ys + 2 * R + BR - 1) / BR;
-    gload(ys - R);
-    int ring_base = 0;  // slot of the first h-row of the current batch
-    for (int b = 0; b < n_batches; ++b) {
-        sstore();
-        __syncthreads();
-        if (b + 1 < n_batches) gload(ys - R + (b + 1) * BR);
-
-        // ---- row pass: warp <-> batch row, 2 groups of 4 adjacent columns per lane
-        {
-            const float *rowp = in_s + warp * INW;
-            int slot = ring_base + warp;
-            if (slot >= RING) slot -= RING;
-            float *outp = ring + slot * TW;
-#pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                const int cidx = g * 128 + 4 * lane;
-                float v[4 + 2 * RP];
-#pragma unroll
-                for (int q = 0; q < (4 + 2 * RP) / 4; ++q) {
-                    const float4 t = *reinterpret_cast<const float4 *>(rowp + cidx + 4 * q);
-                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
-                }
-                float4 o;
-                float *op = reinterpret_cast<float *>(&o);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float acc = taps[0] * v[j + RP];
-#pragma unroll
-                    for (int k = 1; k <= R; ++k) acc = fmaf(taps[k], v[j + RP + k] + v[j + RP - k], acc);
-                    op[j] = acc;
-                }
-                *reinterpret_cast<float4 *>(outp + cidx) = o;
-            }
-        }
-        __syncthreads();
-
-        // ---- column pass: thread <-> column, BR output rows
-        const int yo0 = ys + b * BR - 2 * R;  // output row of t = 0
-        if (yo0 + BR - 1 >= ys) {
-            int base = ring_base + BR;        // oldest slot
-            if (base >= RING) base -= RING;
-            float vals[RING];
-#pragma unroll
-            for (int i = 0; i < RING; ++i) {
-                int s = base + i;
-                if (s >= RING) s -= RING;
-                vals[i] = ring[s * TW + tid];
-            }
-            const int x = x0 + tid;
-#pragma unroll
-            for (int t = 0; t < BR; ++t) {
-                float acc = taps[0] * vals[t + R];
-#pragma unroll
-                for (int k = 1; k <= R; ++k) acc = fmaf(taps[k], vals[t + R + k] + vals[t + R - k], acc);
-                const int yo = yo0 + t;
-                if (yo >= ys && yo < ye && x < w) {
-                    dst[(size_t)yo * pitch + x] = acc;
-                    if (dst2 && !((yo | x) & 1) && (yo >> 1) < h2 && (x >> 1) < w2)
-                        dst2[(size_t)(yo >> 1) * pitch2 + (x >> 1)] = acc;
-                }
-            }
-        }
-        ring_base += BR;
-        if (ring_base >= RING) ring_base -= RING;
-        // the next iteration's first barrier orders this column pass before the
-        // row pass that overwrites the oldest ring slots.
-    }
-}
+#include "blur_strip.cuh"
 
 // Generic tile kernel: any radius <= kMaxBlurRadius, any (tiny) image.
 // 32x32 output tile per CTA, halo tile in shared memory, same arithmetic.
@@ -322,23 +181,33 @@ template <int R>
 static int launch_strip(b200sift_ctx *c, const float *src, float *dst, float *dst2, int n_img, int h, int w,
                         int pitch, size_t img_stride, int h2, int w2, int pitch2, size_t img_stride2, int tapset)
 {
-    constexpr int RP = (R + 3) & ~3;
-    const size_t smem = (size_t)(kStripBR * (kStripW + 2 * RP) + (2 * R + kStripBR) * kStripW) * sizeof(float);
-    const int strips = (w + kStripW - 1) / kStripW;
-    // enough CTAs for >= 2 per SM, segments of >= 64 rows (y-halo re-read <= 2R/64)
-    const int want = (2 * c->sm_count + strips * n_img - 1) / (strips * n_img);
-    int seg = (h + want - 1) / want;
-    seg = ((seg + kStripBR - 1) / kStripBR) * kStripBR;
-    if (seg < 64) seg = 64;
-    if (seg > 512) seg = 512;
-    dim3 grid(strips, (h + seg - 1) / seg, n_img);
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
+    const size_t smem = strip_smem_bytes<R>();
+    static int occ = 0;  // resident CTAs per SM of this instantiation
+    if (!occ) {
         B200_CUDA(cudaFuncSetAttribute(blur_strip_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blur_strip_kernel<R>, 256, smem));
+        if (occ < 1) occ = 1;
     }
+    const int strips = (w + kStripW - 1) / kStripW;
+    const int cols = strips * n_img;
+    // One wave if possible: the largest segment count whose CTAs are all co-resident (segments of
+    // >= 32 rows); larger problems run several waves of 64-row segments (y-halo re-read 2R/64).
+    const int slots = c->sm_count * occ;
+    int n_seg = slots / cols;
+    int seg;
+    if (n_seg >= 1) {
+        seg = (h + n_seg - 1) / n_seg;
+        seg = ((seg + kStripBR - 1) / kStripBR) * kStripBR;
+        if (seg < 32) seg = 32;
+    } else {
+        seg = 64;
+    }
+    if (seg > 4096) seg = 4096;
+    dim3 grid(strips, (h + seg - 1) / seg, n_img);
+    BlurTaps<R> taps;
+    memcpy(taps.t, g_taps[c->device & 15].taps[tapset], sizeof(taps.t));
     blur_strip_kernel<R><<<grid, 256, smem, c->stream>>>(src, dst, dst2, h, w, pitch, img_stride, h2, w2, pitch2,
-                                                         img_stride2, seg, tapset);
+                                                         img_stride2, seg, taps);
     c->launches++;
     B200_CUDA(cudaGetLastError());
     return 0;

@@ -78,16 +78,9 @@ def compute_shift_sift(imgA, imgB, ransac_thr=3, desc_thresh=25000):
     a = np.asarray(imgA)
     b = np.asarray(imgB)
     if a.shape == b.shape and a.dtype == b.dtype:
-        res = sift_impl.detect_and_describe_batch([a, b], ctx=ctx, download=False)
-        n = C.c_int32()
-        na = int(res[0])
-        ia = np.zeros(max(na, 1), np.int32)
-        ib = np.zeros(max(na, 1), np.int32)
-        xy = np.zeros((max(na, 1), 4), np.float32)
-        check(ctx.lib.b200sift_match_images(ctx.handle, 0, 1, int(desc_thresh), ptr(ia), ptr(ib), ptr(xy),
-                                            C.byref(n)))
-        xy = xy[:n.value]
-        matches = [((float(r[0]), float(r[1])), (float(r[2]), float(r[3]))) for r in xy]
+        sift_impl.detect_and_describe_batch([a, b], ctx=ctx, download=False)
+        shifts, nm, _, bp = match_pairs([(0, 1)], ransac_thr, desc_thresh, ctx)
+        return shifts[0], bp[0]
     else:  # different shapes: two passes, host descriptors
         kA, dA = sift_impl.compute_keypoints_and_descriptors(a)
         kB, dB = sift_impl.compute_keypoints_and_descriptors(b)
@@ -114,18 +107,38 @@ def panorama_shifts(images, ransac_thr=3, desc_thresh=25000, ctx=None, return_de
     (and per-pair details when asked)."""
     ctx = ctx or default_context()
     counts = sift_impl.detect_and_describe_batch(images, ctx=ctx, download=False)
-    shifts, details = [], []
-    for i in range(len(images) - 1):
-        na = int(counts[i])
-        n = C.c_int32()
-        ia = np.zeros(max(na, 1), np.int32)
-        ib = np.zeros(max(na, 1), np.int32)
-        xy = np.zeros((max(na, 1), 4), np.float32)
-        check(ctx.lib.b200sift_match_images(ctx.handle, i, i + 1, int(desc_thresh), ptr(ia), ptr(ib), ptr(xy),
-                                            C.byref(n)))
-        mv = (C.c_double * 2)()
-        best = C.c_int32()
-        check(ctx.lib.b200sift_ransac(ctx.handle, ptr(xy), n.value, float(ransac_thr), mv, C.byref(best)))
-        shifts.append((mv[0], mv[1]) if n.value else (0, 0))
-        details.append(dict(n_matches=n.value, ia=ia[:n.value].copy(), ib=ib[:n.value].copy(), best=best.value))
-    return (shifts, counts, details) if return_details else shifts
+    pairs = [(i, i + 1) for i in range(len(images) - 1)]
+    shifts, n_matches, best, _ = match_pairs(pairs, ransac_thr, desc_thresh, ctx)
+    if not return_details:
+        return shifts
+    details = []
+    for p, n in enumerate(n_matches):
+        ia = np.zeros(int(n), np.int32)
+        ib = np.zeros(int(n), np.int32)
+        if n:
+            check(ctx.lib.b200sift_get_pair_matches(ctx.handle, p, ptr(ia), ptr(ib), None))
+        details.append(dict(n_matches=int(n), ia=ia, ib=ib, best=int(best[p])))
+    return shifts, counts, details
+
+
+def match_pairs(pairs, ransac_thr=3, desc_thresh=25000, ctx=None):
+    """Matcher + acceptance + vote for a list of (imgA, imgB) index pairs of the last
+    detect_and_describe_batch, in one device pass.  Returns (shifts [(dx, dy)], n_matches,
+    best_index, best_pairs [((xA,yA),(xB,yB)) or None])."""
+    ctx = ctx or default_context()
+    n = len(pairs)
+    if n == 0:
+        return [], np.zeros(0, np.int32), np.zeros(0, np.int32), []
+    pr = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1, 2))
+    sh = np.zeros((n, 2), np.float64)
+    nm = np.zeros(n, np.int32)
+    best = np.zeros(n, np.int32)
+    xy = np.zeros((n, 4), np.float32)
+    check(ctx.lib.b200sift_match_pairs(ctx.handle, n, pr.ctypes.data_as(C.POINTER(C.c_int32)), int(desc_thresh),
+                                       float(ransac_thr), sh.ctypes.data_as(C.POINTER(C.c_double)),
+                                       nm.ctypes.data_as(C.POINTER(C.c_int32)),
+                                       best.ctypes.data_as(C.POINTER(C.c_int32)), ptr(xy)))
+    shifts = [(float(sh[p, 0]), float(sh[p, 1])) if nm[p] else (0, 0) for p in range(n)]
+    bp = [((float(xy[p, 0]), float(xy[p, 1])), (float(xy[p, 2]), float(xy[p, 3]))) if nm[p] else None
+          for p in range(n)]
+    return shifts, nm, best, bp
