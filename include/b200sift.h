@@ -229,6 +229,12 @@ B200SIFT_API int b200sift_cylindrical_projection(b200sift_ctx *ctx, const uint8_
 B200SIFT_API int b200sift_bench_blur(b200sift_ctx *ctx, int n_img, int h, int w, double sigma, int iters,
                                      int flush_l2, float *ms_per_launch);
 
+/* Measurement hook for the matcher sweep (BASELINE.json config 5): runs `iters` launches of the
+ * tensor-core matcher kernel alone on synthetic nA x nB uint8 descriptors resident in HBM
+ * (already in the packed layout) and returns the mean device time per launch in ms.  top2 != 0
+ * selects the nearest + second-nearest epilogue.  Algorithmic work: 2*128*nA*nB operations. */
+B200SIFT_API int b200sift_bench_match(b200sift_ctx *ctx, int nA, int nB, int top2, int iters, float *ms_per_launch);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,7 @@ PROTOTYPES = {
     'b200sift_remove_duplicates': (_i, [_vp, _vp, _i, _ip]),
     'b200sift_descriptors': (_i, [_vp, C.POINTER(Params), _vp, _i, _pp, _i, _i, _i, _i, _vp]),
     'b200sift_cylindrical_projection': (_i, [_vp, _vp, _i, _i, _i, _d, _vp]),
+    'b200sift_bench_match': (_i, [_vp, _i, _i, _i, _i, C.POINTER(C.c_float)]),
     'b200sift_bench_blur': (_i, [_vp, _i, _i, _i, _d, _i, _i, C.POINTER(C.c_float)]),
 }
 

@@ -147,7 +147,7 @@ void b200sift_destroy(b200sift_ctx *c)
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->pyr.base, c->d_up, c->d_in, c->d_dog, c->d_cand, c->d_loc, c->d_raw, c->d_raw_desc,
                     c->d_sort_idx, c->d_keep, c->d_pos, c->d_cub_tmp, c->d_kps, c->d_desc, c->d_counters,
-                    c->d_mA, c->d_mB, c->d_mout, c->d_nrmB, c->d_misc, c->d_pair};
+                    c->d_mA, c->d_mB, c->d_mout, c->d_nrmB, c->d_misc, c->d_pair, c->d_tc, c->d_tcsrc};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -397,17 +397,12 @@ int b200sift_match_pairs(b200sift_ctx *c, int n_pairs, const int32_t *pairs, int
     c->pair_n = 0;
     if (n_pairs == 0) return 0;
     B200_CUDA(cudaSetDevice(c->device));
-    std::vector<PairDesc> pd(n_pairs);
     for (int p = 0; p < n_pairs; ++p) {
         const int a = pairs[2 * p], b = pairs[2 * p + 1];
         B200_ARG(a >= 0 && a < c->n_img_last && b >= 0 && b < c->n_img_last);
-        pd[p].offA = c->img_off[a];
-        pd[p].nA = c->img_off[a + 1] - c->img_off[a];
-        pd[p].offB = c->img_off[b];
-        pd[p].nB = c->img_off[b + 1] - c->img_off[b];
     }
     Timer tm(c);
-    B200_CHECK(run_match_pairs(c, n_pairs, pd.data(), desc_thresh, vote_thr));
+    B200_CHECK(run_match_pairs(c, n_pairs, pairs, desc_thresh, vote_thr));
     std::vector<PairResult> res(n_pairs);
     B200_CUDA(cudaMemcpyAsync(res.data(), c->d_pair_res, sizeof(PairResult) * n_pairs, cudaMemcpyDeviceToHost,
                               c->stream));
@@ -728,6 +723,13 @@ int b200sift_bench_blur(b200sift_ctx *c, int n_img, int h, int w, double sigma, 
     }
     *ms_per_launch = (float)(acc / iters);
     return 0;
+}
+
+int b200sift_bench_match(b200sift_ctx *c, int nA, int nB, int top2, int iters, float *ms_per_launch)
+{
+    B200_ARG(c && ms_per_launch && nA >= 1 && nB >= 1 && iters >= 1);
+    B200_CUDA(cudaSetDevice(c->device));
+    return bench_match_tc(c, nA, nB, top2, iters, ms_per_launch);
 }
 
 }  // extern "C"

@@ -143,6 +143,8 @@ struct b200sift_ctx {
     int32_t *d_nrmB = nullptr; size_t nrmB_cap = 0;
     void *d_misc = nullptr; size_t misc_cap = 0;
     uint8_t *d_pair = nullptr; size_t pair_cap = 0;   // batched pair matching scratch
+    uint8_t *d_tc = nullptr; size_t tc_cap = 0;       // tensor-core matcher: packed descriptors + norms
+    uint8_t *d_tcsrc = nullptr; size_t tcsrc_cap = 0; // generic match(): A and B side by side
     b200::PairResult *d_pair_res = nullptr; int32_t *d_pair_ia = nullptr, *d_pair_ib = nullptr;
     float *d_pair_xy = nullptr; int pair_rows_max = 0, pair_n = 0;
     std::vector<int> pair_counts;
@@ -190,7 +192,8 @@ int launch_cyl(b200sift_ctx *c, const uint8_t *d_src, int h, int w, int ch, doub
 // match.cu
 int run_match(b200sift_ctx *c, const uint8_t *dA, int nA, const uint8_t *dB, int nB, int32_t *d_best_idx,
               int32_t *d_best_d2, int32_t *d_second_d2);
-int run_match_pairs(b200sift_ctx *c, int n_pairs, const PairDesc *h_pd, int thresh, double vote_thr);
+int run_match_pairs(b200sift_ctx *c, int n_pairs, const int *h_pairs, int thresh, double vote_thr);
+int bench_match_tc(b200sift_ctx *c, int nA, int nB, int top2, int iters, float *ms_kernel);
 int run_accept(b200sift_ctx *c, const int32_t *d_idx, const int32_t *d_d2, int nA, int thresh,
                const b200sift_keypoint *kA, const b200sift_keypoint *kB, int32_t *d_ia, int32_t *d_ib,
                float *d_xyxy, int32_t *d_count);

@@ -1,25 +1,44 @@
-// Brute-force descriptor matcher: for every row of A the nearest and second
-// nearest row of B under squared L2 distance, exact in integers.
+// Brute-force descriptor matcher, host orchestration + the small kernels around the contraction.
 //
-// Replaces /root/reference/image_stitching_sift.py:63-73 (the O(NA*NB) python
-// double loop with np.dot(d,d) and a strict "<" arg-min).  Descriptors are the
-// 0..255 integers generate_descriptors emits (sift_impl.py:519-524), so
-// |a-b|^2 = |a|^2 + |b|^2 - 2 a.b <= 128*255^2 < 2^24 is exact in int32 (and
-// equals the reference's float32 value bit for bit).
-//
-// This file holds the CUDA-core (dp4a) formulation: one thread owns one A row
-// in registers and streams B tiles through shared memory.  B is split into
-// chunks across blockIdx.y so small A sets still fill the GPU; the per-chunk
-// top-2 are merged in chunk order (lowest j wins ties) by a second kernel.
+// Replaces /root/reference/image_stitching_sift.py:63-79 (nearest-neighbour loop + acceptance) and
+// :86-111 (ransac() vote).  The contraction itself runs on the tensor cores (match_tc.cu,
+// tcgen05.mma kind::i8); this file holds
+//   * the merge of per-chunk top-2 results (B is split into chunks so that small problems still
+//     fill the GPU; chunks ascend in j, so a strict "<" keeps the lowest j on ties),
+//   * pair_finalize_kernel: acceptance best < desc_thresh (:74), ordered compaction of the match
+//     list and the translation vote, one CTA per image pair,
+//   * a CUDA-core dp4a formulation of the same contraction, kept as a debugging cross-check
+//     (environment B200SIFT_MATCHER=dp4a); it is not used otherwise.
+// Descriptors are the 0..255 integers generate_descriptors emits (sift_impl.py:519-524), so
+// |a-b|^2 = |a|^2 + |b|^2 - 2 a.b <= 128*255^2 < 2^24 is exact in int32 (and equals the
+// reference's float32 value bit for bit).
 #include <cub/device/device_scan.cuh>
 #include <limits.h>
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace b200 {
 
+// match_tc.cu
+int run_match_tc(b200sift_ctx *c, const uint8_t *d_src, int n_imgs, const int *h_src_off, const int *h_n,
+                 int n_pairs, const int *h_pairs, int rows_max, int n_chunks_out, int tiles_per_chunk, bool top2,
+                 int32_t *d_part);
+void tc_chunking(const b200sift_ctx *c, int rows_max, int nb_max, int n_pairs, int *tiles_per_chunk, int *n_chunks);
+
+static bool use_dp4a()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("B200SIFT_MATCHER");
+        v = (e && strcmp(e, "dp4a") == 0) ? 1 : 0;
+    }
+    return v == 1;
+}
+
 constexpr int kMatchRows = 128;   // A rows per CTA (one per thread)
 constexpr int kMatchTile = 64;    // B rows staged per iteration
-constexpr int kMatchChunk = 512;  // B rows per blockIdx.y
+constexpr int kMatchChunk = 512;  // B rows per blockIdx.y (dp4a path)
 
 __global__ void __launch_bounds__(256) norms_kernel(const uint8_t *__restrict__ d, int n, int32_t *__restrict__ out)
 {
@@ -38,112 +57,11 @@ __global__ void __launch_bounds__(256) norms_kernel(const uint8_t *__restrict__ 
     out[i] = (int32_t)acc;
 }
 
+// dp4a cross-check: one thread owns one A row in registers and streams B tiles through shared memory
 __global__ void __launch_bounds__(kMatchRows)
-match_dp4a_kernel(const uint8_t *__restrict__ A, int nA, const uint8_t *__restrict__ B, int nB,
-                  const int32_t *__restrict__ nrmB, int n_chunks, int32_t *__restrict__ part /*[nA][n_chunks][3]*/)
-{
-    __shared__ uint4 b_s[kMatchTile * 8];
-    __shared__ int32_t nb_s[kMatchTile];
-    const int i = blockIdx.x * kMatchRows + threadIdx.x;
-    const int chunk = blockIdx.y;
-    const int j_begin = chunk * kMatchChunk, j_end = min(nB, j_begin + kMatchChunk);
-    uint32_t a[32];
-    unsigned na = 0;
-    {
-        const int ii = min(i, nA - 1);
-        const uint4 *p = reinterpret_cast<const uint4 *>(A + (size_t)ii * 128);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const uint4 v = p[q];
-            a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
-        }
-#pragma unroll
-        for (int q = 0; q < 32; ++q) na = __dp4a(a[q], a[q], na);
-    }
-    int b1 = INT_MAX, b2 = INT_MAX, bi = -1;
-    for (int j0 = j_begin; j0 < j_end; j0 += kMatchTile) {
-        const int nt = min(kMatchTile, j_end - j0);
-        __syncthreads();
-        for (int t = threadIdx.x; t < nt * 8; t += kMatchRows)
-            b_s[t] = reinterpret_cast<const uint4 *>(B + (size_t)j0 * 128)[t];
-        for (int t = threadIdx.x; t < nt; t += kMatchRows) nb_s[t] = nrmB[j0 + t];
-        __syncthreads();
-        for (int t = 0; t < nt; ++t) {
-            unsigned dot = 0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const uint4 v = b_s[t * 8 + q];
-                dot = __dp4a(a[4 * q], v.x, dot);
-                dot = __dp4a(a[4 * q + 1], v.y, dot);
-                dot = __dp4a(a[4 * q + 2], v.z, dot);
-                dot = __dp4a(a[4 * q + 3], v.w, dot);
-            }
-            const int d = (int)na + nb_s[t] - 2 * (int)dot;
-            if (d < b1) { b2 = b1; b1 = d; bi = j0 + t; }
-            else if (d < b2) b2 = d;
-        }
-    }
-    if (i < nA) {
-        int32_t *o = part + ((size_t)i * n_chunks + chunk) * 3;
-        o[0] = bi; o[1] = b1; o[2] = b2;
-    }
-}
-
-__global__ void __launch_bounds__(256)
-match_merge_kernel(const int32_t *__restrict__ part, int nA, int n_chunks, int32_t *__restrict__ best_idx,
-                   int32_t *__restrict__ best_d2, int32_t *__restrict__ second_d2)
-{
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= nA) return;
-    int b1 = INT_MAX, b2 = INT_MAX, bi = -1;
-    for (int c = 0; c < n_chunks; ++c) {
-        const int32_t *o = part + ((size_t)i * n_chunks + c) * 3;
-        const int ci = o[0], c1 = o[1], c2 = o[2];
-        if (ci < 0) continue;
-        if (c1 < b1) { b2 = min(b1, c2); b1 = c1; bi = ci; }
-        else { b2 = min(b2, c1); }
-    }
-    best_idx[i] = bi;
-    best_d2[i] = b1;
-    if (second_d2) second_d2[i] = b2;
-}
-
-int run_match(b200sift_ctx *c, const uint8_t *dA, int nA, const uint8_t *dB, int nB, int32_t *d_best_idx,
-              int32_t *d_best_d2, int32_t *d_second_d2)
-{
-    if (nA <= 0) return 0;
-    const int n_chunks = nB > 0 ? (nB + kMatchChunk - 1) / kMatchChunk : 1;
-    size_t cap = c->nrmB_cap;
-    B200_CHECK(ensure(&c->d_nrmB, &cap, (size_t)(nB > 0 ? nB : 1)));
-    c->nrmB_cap = cap;
-    cap = c->mout_cap;
-    B200_CHECK(ensure(&c->d_mout, &cap, (size_t)nA * n_chunks * 3));
-    c->mout_cap = cap;
-    if (nB > 0) {
-        norms_kernel<<<(nB + 255) / 256, 256, 0, c->stream>>>(dB, nB, c->d_nrmB);
-        c->launches++;
-    }
-    dim3 grid((nA + kMatchRows - 1) / kMatchRows, n_chunks);
-    match_dp4a_kernel<<<grid, kMatchRows, 0, c->stream>>>(dA, nA, dB, nB, c->d_nrmB, n_chunks, c->d_mout);
-    match_merge_kernel<<<(nA + 255) / 256, 256, 0, c->stream>>>(c->d_mout, nA, n_chunks, d_best_idx, d_best_d2,
-                                                                d_second_d2);
-    c->launches += 2;
-    B200_CUDA(cudaGetLastError());
-    return 0;
-}
-
-// ---------------------------------------------------------------------------
-// Batched form: every requested pair of the last detect in one pass
-// (image_stitching_sift.py:312-327 runs compute_shift_sift per adjacent pair).
-//   match_pairs_kernel   grid (row tiles, B chunks, pairs): per-chunk top-2
-//   pair_finalize_kernel one CTA per pair: merge the chunks, accept best < thresh
-//                        (:74), compact in A order (block scan), then the ransac()
-//                        vote (:86-111, float64, first maximum wins).
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kMatchRows)
-match_pairs_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__ nrm,
-                   const PairDesc *__restrict__ pd, int n_chunks_max, int rows_max,
-                   int32_t *__restrict__ part /*[pair][rows_max][n_chunks_max][3]*/)
+match_pairs_kernel(const uint8_t *__restrict__ descA, const uint8_t *__restrict__ descB,
+                   const int32_t *__restrict__ nrmB_all, const PairDesc *__restrict__ pd, int n_chunks_max,
+                   int rows_max, int32_t *__restrict__ part /*[pair][rows_max][n_chunks_max][3]*/)
 {
     __shared__ uint4 b_s[kMatchTile * 8];
     __shared__ int32_t nb_s[kMatchTile];
@@ -151,9 +69,8 @@ match_pairs_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__
     const int chunk = blockIdx.y;
     if ((int)(blockIdx.x * kMatchRows) >= P.nA) return;
     const int j_begin = chunk * kMatchChunk, j_end = min(P.nB, j_begin + kMatchChunk);
-    if (j_begin >= P.nB && chunk > 0) return;
-    const uint8_t *A = desc + (size_t)P.offA * 128, *B = desc + (size_t)P.offB * 128;
-    const int32_t *nrmB = nrm + P.offB;
+    const uint8_t *A = descA + (size_t)P.offA * 128, *B = descB + (size_t)P.offB * 128;
+    const int32_t *nrmB = nrmB_all + P.offB;
     const int i = blockIdx.x * kMatchRows + threadIdx.x;
     uint32_t a[32];
     unsigned na = 0;
@@ -197,6 +114,84 @@ match_pairs_kernel(const uint8_t *__restrict__ desc, const int32_t *__restrict__
     }
 }
 
+// per-chunk (best j, best d, second d) -> global top-2; chunks ascend in j
+__global__ void __launch_bounds__(256)
+match_merge_kernel(const int32_t *__restrict__ part, int nA, int n_chunks, int32_t *__restrict__ best_idx,
+                   int32_t *__restrict__ best_d2, int32_t *__restrict__ second_d2)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= nA) return;
+    int b1 = INT_MAX, b2 = INT_MAX, bi = -1;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int32_t *o = part + ((size_t)i * n_chunks + c) * 3;
+        const int ci = o[0], c1 = o[1], c2 = o[2];
+        if (ci < 0) continue;
+        if (c1 < b1) { b2 = min(b1, c2); b1 = c1; bi = ci; }
+        else { b2 = min(b2, c1); }
+    }
+    best_idx[i] = bi;
+    best_d2[i] = b1;
+    if (second_d2) second_d2[i] = b2;
+}
+
+// Generic A (nA,128) x B (nB,128), device pointers, row-major uint8.
+int run_match(b200sift_ctx *c, const uint8_t *dA, int nA, const uint8_t *dB, int nB, int32_t *d_best_idx,
+              int32_t *d_best_d2, int32_t *d_second_d2)
+{
+    if (nA <= 0) return 0;
+    size_t cap;
+    if (use_dp4a()) {
+        const int n_chunks = nB > 0 ? (nB + kMatchChunk - 1) / kMatchChunk : 1;
+        cap = c->nrmB_cap;
+        B200_CHECK(ensure(&c->d_nrmB, &cap, (size_t)(nB > 0 ? nB : 1)));
+        c->nrmB_cap = cap;
+        cap = c->mout_cap;
+        B200_CHECK(ensure(&c->d_mout, &cap, (size_t)nA * n_chunks * 3 + 16));
+        c->mout_cap = cap;
+        PairDesc pd{0, nA, 0, nB};
+        PairDesc *d_pd = reinterpret_cast<PairDesc *>(c->d_mout + (size_t)nA * n_chunks * 3);
+        B200_CUDA(cudaMemcpyAsync(d_pd, &pd, sizeof(pd), cudaMemcpyHostToDevice, c->stream));
+        B200_CUDA(cudaStreamSynchronize(c->stream));
+        if (nB > 0) norms_kernel<<<(nB + 255) / 256, 256, 0, c->stream>>>(dB, nB, c->d_nrmB);
+        dim3 grid((nA + kMatchRows - 1) / kMatchRows, n_chunks, 1);
+        match_pairs_kernel<<<grid, kMatchRows, 0, c->stream>>>(dA, dB, c->d_nrmB, d_pd, n_chunks, nA, c->d_mout);
+        match_merge_kernel<<<(nA + 255) / 256, 256, 0, c->stream>>>(c->d_mout, nA, n_chunks, d_best_idx, d_best_d2,
+                                                                    d_second_d2);
+        c->launches += 3;
+        B200_CUDA(cudaGetLastError());
+        return 0;
+    }
+    // tensor-core path: A and B become "image" 0 and 1 of one packed buffer
+    int tpc, n_chunks;
+    tc_chunking(c, nA, nB, 1, &tpc, &n_chunks);
+    cap = c->mout_cap;
+    B200_CHECK(ensure(&c->d_mout, &cap, (size_t)nA * n_chunks * 3));
+    c->mout_cap = cap;
+    // both sets must be addressable from one base pointer: stage them side by side
+    cap = c->tcsrc_cap;
+    B200_CHECK(ensure(&c->d_tcsrc, &cap, (size_t)(nA + (nB > 0 ? nB : 0)) * 128));
+    c->tcsrc_cap = cap;
+    B200_CUDA(cudaMemcpyAsync(c->d_tcsrc, dA, (size_t)nA * 128, cudaMemcpyDeviceToDevice, c->stream));
+    if (nB > 0)
+        B200_CUDA(cudaMemcpyAsync(c->d_tcsrc + (size_t)nA * 128, dB, (size_t)nB * 128, cudaMemcpyDeviceToDevice,
+                                  c->stream));
+    const int src_off[2] = {0, nA}, ns[2] = {nA, nB}, pr[2] = {0, 1};
+    B200_CHECK(run_match_tc(c, c->d_tcsrc, 2, src_off, ns, 1, pr, nA, n_chunks, tpc, d_second_d2 != nullptr,
+                            c->d_mout));
+    match_merge_kernel<<<(nA + 255) / 256, 256, 0, c->stream>>>(c->d_mout, nA, n_chunks, d_best_idx, d_best_d2,
+                                                                d_second_d2);
+    c->launches++;
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Batched form: every requested pair of the last detect in one pass
+// (image_stitching_sift.py:312-327 runs compute_shift_sift per adjacent pair).
+// pair_finalize_kernel: one CTA per pair merges the chunks, accepts best < thresh (:74),
+// compacts in A order (block scan), then runs the ransac() vote (:86-111, float64, first
+// maximum wins).
+// ---------------------------------------------------------------------------
 constexpr int kFinThreads = 1024;
 
 __global__ void __launch_bounds__(kFinThreads)
@@ -210,7 +205,6 @@ pair_finalize_kernel(const PairDesc *__restrict__ pd, const int32_t *__restrict_
     __shared__ unsigned long long s_red[32];
     const int pair = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const PairDesc P = pd[pair];
-    const int nck = P.nB > 0 ? (P.nB + kMatchChunk - 1) / kMatchChunk : 1;
     const b200sift_keypoint *kA = kps + P.offA, *kB = kps + P.offB;
     const size_t mo = (size_t)pair * rows_max;
     if (tid == 0) s_base = 0;
@@ -220,7 +214,7 @@ pair_finalize_kernel(const PairDesc *__restrict__ pd, const int32_t *__restrict_
         int b1 = INT_MAX, bi = -1;
         if (i < P.nA) {
             const int32_t *o = part + ((size_t)pair * rows_max + i) * n_chunks_max * 3;
-            for (int c = 0; c < nck; ++c) {
+            for (int c = 0; c < n_chunks_max; ++c) {
                 const int ci = o[3 * c], c1 = o[3 * c + 1];
                 if (ci >= 0 && c1 < b1) { b1 = c1; bi = ci; }   // strict <: the earlier chunk (lower j) wins ties
             }
@@ -287,22 +281,30 @@ pair_finalize_kernel(const PairDesc *__restrict__ pd, const int32_t *__restrict_
     }
 }
 
-// norms of all final descriptors + both kernels above; results land in c->d_pair_res.
-int run_match_pairs(b200sift_ctx *c, int n_pairs, const PairDesc *h_pd, int thresh, double vote_thr)
+// Matcher + finalize for n_pairs (imgA, imgB) index pairs of the last detect; results land in
+// c->d_pair_res / c->d_pair_ia / ...
+int run_match_pairs(b200sift_ctx *c, int n_pairs, const int *h_pairs, int thresh, double vote_thr)
 {
-    int rows_max = 1, nb_max = 1, n_total = c->img_off.empty() ? 0 : c->img_off.back();
+    const int n_img = c->n_img_last;
+    std::vector<PairDesc> h_pd(n_pairs);
+    int rows_max = 1, nb_max = 0;
     for (int p = 0; p < n_pairs; ++p) {
+        const int a = h_pairs[2 * p], b = h_pairs[2 * p + 1];
+        h_pd[p].offA = c->img_off[a];
+        h_pd[p].nA = c->img_off[a + 1] - c->img_off[a];
+        h_pd[p].offB = c->img_off[b];
+        h_pd[p].nB = c->img_off[b + 1] - c->img_off[b];
         rows_max = h_pd[p].nA > rows_max ? h_pd[p].nA : rows_max;
         nb_max = h_pd[p].nB > nb_max ? h_pd[p].nB : nb_max;
     }
-    const int n_chunks = (nb_max + kMatchChunk - 1) / kMatchChunk;
-    size_t cap = c->nrmB_cap;
-    B200_CHECK(ensure(&c->d_nrmB, &cap, (size_t)(n_total > 0 ? n_total : 1)));
-    c->nrmB_cap = cap;
-    cap = c->mout_cap;
+    const int n_total = c->img_off.empty() ? 0 : c->img_off.back();
+    int tpc = 1, n_chunks;
+    if (use_dp4a()) n_chunks = nb_max > 0 ? (nb_max + kMatchChunk - 1) / kMatchChunk : 1;
+    else tc_chunking(c, rows_max, nb_max, n_pairs, &tpc, &n_chunks);
+    size_t cap = c->mout_cap;
     B200_CHECK(ensure(&c->d_mout, &cap, (size_t)n_pairs * rows_max * n_chunks * 3));
     c->mout_cap = cap;
-    // per-pair scratch: pd | res | ia | ib | xy | mv
+    // per-pair scratch: mv | res | xy | pd | ia | ib
     const size_t rows = (size_t)n_pairs * rows_max;
     const size_t bytes = (size_t)n_pairs * (sizeof(PairDesc) + sizeof(PairResult)) + rows * (4 + 4 + 16 + 16) + 256;
     cap = c->pair_cap;
@@ -318,21 +320,32 @@ int run_match_pairs(b200sift_ctx *c, int n_pairs, const PairDesc *h_pd, int thre
     c->pair_rows_max = rows_max;
     c->pair_n = n_pairs;
     c->d_pair_res = res; c->d_pair_ia = m_ia; c->d_pair_ib = m_ib; c->d_pair_xy = m_xy;
-    B200_CUDA(cudaMemcpyAsync(pd, h_pd, sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, c->stream));
-    if (n_total > 0) {
-        norms_kernel<<<(n_total + 255) / 256, 256, 0, c->stream>>>(c->d_desc, n_total, c->d_nrmB);
-        c->launches++;
+    B200_CUDA(cudaMemcpyAsync(pd, h_pd.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, c->stream));
+    if (use_dp4a()) {
+        cap = c->nrmB_cap;
+        B200_CHECK(ensure(&c->d_nrmB, &cap, (size_t)(n_total > 0 ? n_total : 1)));
+        c->nrmB_cap = cap;
+        if (n_total > 0) norms_kernel<<<(n_total + 255) / 256, 256, 0, c->stream>>>(c->d_desc, n_total, c->d_nrmB);
+        dim3 grid((rows_max + kMatchRows - 1) / kMatchRows, n_chunks, n_pairs);
+        match_pairs_kernel<<<grid, kMatchRows, 0, c->stream>>>(c->d_desc, c->d_desc, c->d_nrmB, pd, n_chunks, rows_max,
+                                                              c->d_mout);
+        c->launches += 2;
+        B200_CUDA(cudaStreamSynchronize(c->stream));  // h_pd is read by the async copy above
+    } else {
+        std::vector<int> off(n_img), cnt(n_img);
+        for (int i = 0; i < n_img; ++i) { off[i] = c->img_off[i]; cnt[i] = c->img_off[i + 1] - c->img_off[i]; }
+        B200_CHECK(run_match_tc(c, c->d_desc, n_img, off.data(), cnt.data(), n_pairs, h_pairs, rows_max, n_chunks, tpc,
+                                false, c->d_mout));
     }
-    dim3 grid((rows_max + kMatchRows - 1) / kMatchRows, n_chunks, n_pairs);
-    match_pairs_kernel<<<grid, kMatchRows, 0, c->stream>>>(c->d_desc, c->d_nrmB, pd, n_chunks, rows_max, c->d_mout);
     pair_finalize_kernel<<<n_pairs, kFinThreads, 0, c->stream>>>(pd, c->d_mout, n_chunks, rows_max, c->d_kps, thresh,
                                                                 vote_thr, m_ia, m_ib, m_xy, m_mv, res);
-    c->launches += 2;
+    c->launches++;
     B200_CUDA(cudaGetLastError());
     return 0;
 }
 
-// accepted matches of image_stitching_sift.py:74-79, compacted in A order
+// accepted matches of image_stitching_sift.py:74-79, compacted in A order (single pair, used by
+// b200sift_match_images)
 __global__ void __launch_bounds__(256)
 accept_flag_kernel(const int32_t *__restrict__ best_idx, const int32_t *__restrict__ best_d2, int nA, int thresh,
                    uint32_t *__restrict__ keep)
