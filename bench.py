@@ -178,6 +178,9 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.pop('NCCL_DEBUG', None)     # its version banner goes to stdout; keep that to the one JSON line
+        if os.environ.get('B200SIFT_NCCL_DEBUG'):
+            os.environ['NCCL_DEBUG'] = os.environ['B200SIFT_NCCL_DEBUG']
         dist.init_process_group('nccl', device_id=dev)
     ctx = _capi.default_context(local)
     stream = torch.cuda.Stream(dev)
@@ -191,16 +194,14 @@ def main():
     pinned_np = [t.numpy() for t in pinned]
     resident = [t.to(dev) for t in pinned]                                # value-leg inputs (HBM)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    ops = panorama.gpu_ops(ctx)
+    backend = panorama.GpuBackend(ctx)
     lo, hi = panorama.shard_range(n, rank, world)
 
     def step_resident():
         """inputs in HBM; per-pair results stay on the device except counts / the voted shift."""
         if world == 1:
             return iss.panorama_shifts(resident, ctx=ctx, return_details=True)
-        dops = panorama.Ops(lambda ims: sift_impl.detect_and_describe_batch(ims, ctx=ctx) if len(ims) else [],
-                            ops.match, ops.vote)
-        return panorama.sharded_panorama_shifts(resident, dops, dist=dist, device=dev)
+        return panorama.sharded_panorama_shifts(resident, backend, dist=dist, device=dev)
 
     def step_e2e():
         """host images in, host keypoints + descriptors + shifts out."""
@@ -208,7 +209,9 @@ def main():
             shifts, counts, det = iss.panorama_shifts(pinned_np, ctx=ctx, return_details=True)
             res = sift_impl.download_results(counts, ctx)
             return shifts, counts, res
-        return panorama.sharded_panorama_shifts(pinned_np, ops, dist=dist, device=dev)
+        shifts, counts = panorama.sharded_panorama_shifts(pinned_np, backend, dist=dist, device=dev)
+        res = sift_impl.download_results(backend.counts, ctx)       # this rank's block, to the host
+        return shifts, counts, res
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):

@@ -159,6 +159,14 @@ B200SIFT_API int b200sift_match_pairs(b200sift_ctx *ctx, int n_pairs, const int3
  * ia / ib keypoint indices and xyxy (n x 4); capacity n_matches[p]. */
 B200SIFT_API int b200sift_get_pair_matches(b200sift_ctx *ctx, int p, int32_t *ia, int32_t *ib, float *xyxy);
 
+/* Append an externally produced result set (n descriptors (n,128) uint8 + n (x,y) float32 pairs)
+ * to the results of the last detect_describe as an extra image, so that pairs against it can be
+ * part of b200sift_match_pairs.  This is how a rank matches its last image against the first
+ * image of the next rank after the NCCL all-gather.  on_device: the pointers are
+ * device pointers of this context's GPU.  *image_index receives the new image's index. */
+B200SIFT_API int b200sift_append_results(b200sift_ctx *ctx, const uint8_t *desc, const float *xy, int n,
+                                         int on_device, int32_t *image_index);
+
 /* ransac() translation vote (image_stitching_sift.py:86-111) on the device:
  * matches n x 4 float (xA,yA,xB,yB); returns the winning index in *best
  * (first maximum; -1 when n == 0) and its (dx,dy) in move[2]. */

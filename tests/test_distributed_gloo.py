@@ -18,26 +18,44 @@ def _free_port():
     return p
 
 
-def _oracle_ops():
-    from oracle import sift_oracle as so
-    from vfx_image_stitching_b200.panorama import Ops
+class OracleBackend:
+    """The backend interface of panorama.py with the CPU oracle playing the kernels."""
 
-    def detect(images):
-        out = []
+    def __init__(self):
+        from oracle import sift_oracle as so
+        self.so = so
+        self.res = []
+
+    def detect(self, images):
+        self.res = []
         for im in images:
-            k, d = so.compute_keypoints_and_descriptors(im)
-            out.append((k, np.asarray(d, np.float32).reshape(-1, 128).astype(np.uint8)))
+            k, d = self.so.compute_keypoints_and_descriptors(im)
+            self.res.append((np.stack([k['x'], k['y']], 1).astype(np.float32).reshape(-1, 2),
+                             np.asarray(d, np.float32).reshape(-1, 128).astype(np.uint8)))
+        return np.array([len(d) for _, d in self.res], np.int32)
+
+    def first_image(self, device):
+        import torch
+        if not self.res:
+            return torch.zeros((0, 128), dtype=torch.uint8), torch.zeros((0, 2), dtype=torch.float32)
+        xy, d = self.res[0]
+        return torch.from_numpy(d.copy()), torch.from_numpy(xy.copy())
+
+    def append_remote(self, desc, xy):
+        self.res.append((xy.numpy().copy(), desc.numpy().copy()))
+        return len(self.res) - 1
+
+    def match_pairs(self, pairs, ransac_thr, desc_thresh):
+        out = []
+        for a, b in pairs:
+            (xa, da), (xb, db) = self.res[a], self.res[b]
+            idx, d1, _ = self.so.match_u8(da, db)
+            keep = (d1 < desc_thresh) & (idx != -1)
+            ia = np.nonzero(keep)[0]
+            ib = idx[keep]
+            m = np.concatenate([xa[ia], xb[ib]], 1).astype(np.float64) if len(ia) else np.zeros((0, 4))
+            out.append(tuple(self.so.ransac(m, ransac_thr)[0]))
         return out
-
-    def match(kA, dA, kB, dB, thresh):
-        idx, d1, _ = so.match_u8(dA, dB)
-        keep = (d1 < thresh) & (idx != -1)
-        ia = np.nonzero(keep)[0]
-        ib = idx[keep]
-        return np.stack([kA['x'][ia], kA['y'][ia], kB['x'][ib], kB['y'][ib]], 1).astype(np.float64) \
-            if len(ia) else np.zeros((0, 4))
-
-    return Ops(detect, match, lambda m, thr: so.ransac(m, thr)[0])
 
 
 def _images():
@@ -53,7 +71,7 @@ def _worker(rank, world, port, q):
     from vfx_image_stitching_b200.panorama import sharded_panorama_shifts
     dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
     try:
-        shifts, counts = sharded_panorama_shifts(_images(), _oracle_ops(), dist=dist, device='cpu')
+        shifts, counts = sharded_panorama_shifts(_images(), OracleBackend(), dist=dist, device='cpu')
         q.put((rank, shifts, counts))
     finally:
         dist.destroy_process_group()
@@ -72,7 +90,7 @@ def test_shard_ranges():
 def test_sharded_equals_single_process(world):
     import torch.multiprocessing as mp
     from vfx_image_stitching_b200.panorama import sharded_panorama_shifts
-    ref_shifts, ref_counts = sharded_panorama_shifts(_images(), _oracle_ops())
+    ref_shifts, ref_counts = sharded_panorama_shifts(_images(), OracleBackend())
     assert len(ref_shifts) == 4 and sum(abs(abs(s[0]) - 40) < 1.0 and abs(abs(s[1]) - 2) < 1.0 for s in ref_shifts) >= 3
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
@@ -80,7 +98,7 @@ def test_sharded_equals_single_process(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=240) for _ in range(world)]
+    got = [q.get(timeout=90) for _ in range(world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0

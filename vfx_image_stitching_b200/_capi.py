@@ -55,6 +55,7 @@ PROTOTYPES = {
     'b200sift_match_images': (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _ip]),
     'b200sift_match_pairs': (_i, [_vp, _i, _ip, _i, _d, C.POINTER(C.c_double), _ip, _ip, _vp]),
     'b200sift_get_pair_matches': (_i, [_vp, _i, _vp, _vp, _vp]),
+    'b200sift_append_results': (_i, [_vp, _vp, _vp, _i, _i, _ip]),
     'b200sift_ransac': (_i, [_vp, _vp, _i, _d, C.POINTER(C.c_double), _ip]),
     'b200sift_gaussian_blur': (_i, [_vp, _vp, _i, _i, _d, _vp, _i]),
     'b200sift_base_image': (_i, [_vp, _vp, _i, _i, _d, _d, _vp]),

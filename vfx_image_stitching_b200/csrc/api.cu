@@ -437,6 +437,47 @@ int b200sift_get_pair_matches(b200sift_ctx *c, int p, int32_t *ia, int32_t *ib, 
     return 0;
 }
 
+int b200sift_append_results(b200sift_ctx *c, const uint8_t *desc, const float *xy, int n, int on_device,
+                            int32_t *image_index)
+{
+    B200_ARG(c && image_index && n >= 0 && (n == 0 || (desc && xy)));
+    if (!c->have_results) {
+        set_error("append_results before a successful detect_describe");
+        return B200SIFT_ESTATE;
+    }
+    B200_CUDA(cudaSetDevice(c->device));
+    const int used = c->img_off.back();
+    if (used + n > c->out_cap) {  // grow the compact result arrays, keeping their contents
+        const int ncap = used + n + (used + n) / 4 + 1024;
+        b200sift_keypoint *nk = nullptr;
+        uint8_t *nd = nullptr;
+        B200_CUDA(cudaMalloc((void **)&nk, sizeof(b200sift_keypoint) * (size_t)ncap));
+        B200_CUDA(cudaMalloc((void **)&nd, (size_t)ncap * 128));
+        B200_CUDA(cudaMemcpyAsync(nk, c->d_kps, sizeof(b200sift_keypoint) * (size_t)used, cudaMemcpyDeviceToDevice,
+                                  c->stream));
+        B200_CUDA(cudaMemcpyAsync(nd, c->d_desc, (size_t)used * 128, cudaMemcpyDeviceToDevice, c->stream));
+        B200_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_kps);
+        cudaFree(c->d_desc);
+        c->d_kps = nk;
+        c->d_desc = nd;
+        c->out_cap = ncap;
+    }
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (n > 0) {
+        B200_CUDA(cudaMemcpyAsync(c->d_desc + (size_t)used * 128, desc, (size_t)n * 128, kind, c->stream));
+        B200_CUDA(cudaMemsetAsync(c->d_kps + used, 0, sizeof(b200sift_keypoint) * (size_t)n, c->stream));
+        // (x, y) are the first two floats of the 24-byte keypoint record
+        B200_CUDA(cudaMemcpy2DAsync(c->d_kps + used, sizeof(b200sift_keypoint), xy, 2 * sizeof(float),
+                                    2 * sizeof(float), n, kind, c->stream));
+        if (!on_device) B200_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    *image_index = c->n_img_last;
+    c->img_off.push_back(used + n);
+    c->n_img_last += 1;
+    return 0;
+}
+
 int b200sift_ransac(b200sift_ctx *c, const float *matches, int n, double thr, double *move, int32_t *best)
 {
     B200_ARG(c && move && best && n >= 0);
