@@ -147,7 +147,7 @@ void b200sift_destroy(b200sift_ctx *c)
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->pyr.base, c->d_up, c->d_in, c->d_dog, c->d_cand, c->d_loc, c->d_raw, c->d_raw_desc,
                     c->d_sort_idx, c->d_keep, c->d_pos, c->d_cub_tmp, c->d_kps, c->d_desc, c->d_counters,
-                    c->d_mA, c->d_mB, c->d_mout, c->d_nrmB, c->d_misc, c->d_pair, c->d_tc, c->d_tcsrc};
+                    c->d_mA, c->d_mB, c->d_mout, c->d_nrmB, c->d_misc, c->d_pair, c->d_tc, c->d_tcsrc, c->d_seg};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->h_counters) cudaFreeHost(c->h_counters);

@@ -127,6 +127,7 @@ struct b200sift_ctx {
     uint8_t *d_raw_desc = nullptr;                 // [raw_cap][128]
     uint32_t *d_sort_idx = nullptr; uint32_t *d_keep = nullptr; uint32_t *d_pos = nullptr;
     void *d_cub_tmp = nullptr; size_t cub_tmp_cap = 0;
+    int *d_seg = nullptr; size_t seg_cap = 0; std::vector<int> h_seg;   // per-image segments of the sort
     b200sift_keypoint *d_kps = nullptr;            // final, compact, image-major
     uint8_t *d_desc = nullptr;                     // final [n][128]
     int out_cap = 0;
@@ -180,7 +181,7 @@ int build_octaves(b200sift_ctx *c, const double *sigmas);
 int base_blur(b200sift_ctx *c, const float *d_up, double sigma_diff);
 int launch_dog(b200sift_ctx *c, const float *a, const float *b, float *out, size_t n);
 // detect.cu
-PyrView make_view(const Pyramid &p);
+PyrView make_view(const b200sift_ctx *c);
 DetectParams make_detect_params(const b200sift_params &p);
 int run_detect(b200sift_ctx *c, const b200sift_params &p, int want_scan_order);
 int run_describe(b200sift_ctx *c, const b200sift_params &p, const RawKeypoint *d_raw, int n, int converted,

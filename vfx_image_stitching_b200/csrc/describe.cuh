@@ -27,7 +27,7 @@ constexpr size_t kDescSmemPerWarp = kDescHistFloats * sizeof(float) + 2 * kDescQ
 
 __global__ void __launch_bounds__(kDescWarps * 32, 3)
 describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw, int n, int converted,
-                uint8_t *__restrict__ desc_out)
+                uint8_t *__restrict__ desc_out, int32_t *__restrict__ work_counter)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -36,7 +36,14 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
     int *qy = qx + kDescQueue;
     const int warps_total = gridDim.x * kDescWarps;
     const unsigned lt_mask = (1u << lane) - 1u;
-    for (int ki = blockIdx.x * kDescWarps + wib; ki < n; ki += warps_total) {
+    (void)warps_total;
+    // keypoint windows differ 6x in size: warps take the next keypoint from a global counter
+    // instead of a static stride, which removes the tail where a few warps still work
+    for (;;) {
+        int ki = 0;
+        if (lane == 0) ki = atomicAdd(work_counter, 1);
+        ki = __shfl_sync(0xffffffffu, ki, 0);
+        if (ki >= n) break;
         const RawKeypoint K = raw[ki];
         // convert_keypoints_to_input_image_size (:333-343) unless already done
         const float kx = converted ? K.x : K.x * 0.5f, ky = converted ? K.y : K.y * 0.5f;

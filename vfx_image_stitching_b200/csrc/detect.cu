@@ -20,10 +20,11 @@
 namespace b200 {
 
 // counters layout
-enum { CNT_CAND = 0, CNT_LOC = 1, CNT_RAW = 2, CNT_OUT = 3, CNT_HDR = 8, CNT_PER_IMG = 4 };
+enum { CNT_CAND = 0, CNT_LOC = 1, CNT_RAW = 2, CNT_OUT = 3, CNT_WORK_DESC = 4, CNT_WORK_ORI = 5, CNT_HDR = 8, CNT_PER_IMG = 4 };
 
-PyrView make_view(const Pyramid &p)
+PyrView make_view(const b200sift_ctx *c)
 {
+    const Pyramid &p = c->pyr;
     PyrView v;
     v.n_img = p.n_img;
     v.n_oct = p.n_oct;
@@ -415,15 +416,6 @@ refine_kernel(PyrView v, DetectParams dp, const Candidate *__restrict__ cand, in
     }
 }
 
-// ---------------------------------------------------------------------------
-// orientation assignment (sift_impl.py:246-293), one warp per localized
-// extremum.  Each lane accumulates its share of the (2r+1)^2 window into a
-// private float64 36-bin histogram in shared memory ([bin][lane], bank
-// conflict free); the lanes' histograms are then summed in a fixed order, so
-// the result is deterministic (no atomics).
-// ---------------------------------------------------------------------------
-constexpr int kOriWarps = 4;
-constexpr int kOriMaxBins = 36;
 #define B200_RAD2DEGF (180.0f / 3.141592653589793238462643383279502884f)
 
 __device__ __forceinline__ float mod360f(float a)  // np.float32 % 360 for |a| < 360
@@ -433,6 +425,15 @@ __device__ __forceinline__ float mod360f(float a)  // np.float32 % 360 for |a| <
     return a;
 }
 
+// ---------------------------------------------------------------------------
+// orientation assignment (sift_impl.py:246-293), one warp per localized
+// extremum.  Each lane accumulates its share of the (2r+1)^2 window into a
+// private float64 36-bin histogram in shared memory ([bin][lane], bank
+// conflict free); the lanes' histograms are then summed in a fixed order, so
+// the result is deterministic (no atomics).
+// ---------------------------------------------------------------------------
+constexpr int kOriWarps = 4;
+constexpr int kOriMaxBins = 36;
 __global__ void __launch_bounds__(kOriWarps * 32)
 orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int loc_cap,
               RawKeypoint *__restrict__ raw, int raw_cap, int32_t *__restrict__ counters)
@@ -445,7 +446,12 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
     const int n = min(counters[CNT_LOC], loc_cap);
     const int warps_total = gridDim.x * kOriWarps;
     double(*hist)[32] = hist_s[wib];
-    for (int li = blockIdx.x * kOriWarps + wib; li < n; li += warps_total) {
+    (void)warps_total;
+    for (;;) {  // dynamic work queue: windows are (2r+1)^2 with r = 7..17
+        int li = 0;
+        if (lane == 0) li = atomicAdd(&counters[CNT_WORK_ORI], 1);
+        li = __shfl_sync(0xffffffffu, li, 0);
+        if (li >= n) break;
         const Localized L = loc[li];
         const int img = L.img_o_l >> 16, o = (L.img_o_l >> 8) & 255, layer = L.img_o_l & 255;
         const int h = v.h[o], w = v.w[o], pitch = v.pitch[o];
@@ -462,19 +468,30 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
         const int nx = xhi - xlo + 1, ny = yhi - ylo + 1;
         const int total = (nx > 0 && ny > 0) ? nx * ny : 0;
         int yy = lane / max(nx, 1), xx = lane - yy * max(nx, 1);
-        for (int idx = lane; idx < total; idx += 32) {
-            const int y = ylo + yy, x = xlo + xx;
-            const int dy = y - cy, dx = x - cx;
-            xx += 32;
-            while (xx >= nx) { xx -= nx; ++yy; }
-            const float *p = gimg + (size_t)y * pitch + x;
-            const float gx = p[1] - p[-1];
-            const float gy = p[-pitch] - p[pitch];
-            const float mag = sqrtf(gx * gx + gy * gy);
-            const float ang = mod360f(atan2f(gy, gx) * B200_RAD2DEGF);
-            const float wgt = expf(weight_fac * (float)(dx * dx + dy * dy));
-            const int bin = (int)rintf(ang * (float)nb / 360.f) % nb;
-            hist[bin][lane] += (double)(wgt * mag);
+        // two pixels per lane and iteration (straight-line code: the two gather / sqrt / atan2 / exp
+        // chains overlap); the histogram updates stay in pixel order
+        for (int idx = lane; idx < total; idx += 64) {
+            int bin[2];
+            float val[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const bool live = idx + 32 * u < total;
+                const int y = live ? ylo + yy : ylo, x = live ? xlo + xx : xlo;
+                const int dy = y - cy, dx = x - cx;
+                xx += 32;
+                while (xx >= nx) { xx -= nx; ++yy; }
+                const float *p = gimg + (size_t)y * pitch + x;
+                const float gx = p[1] - p[-1];
+                const float gy = p[-pitch] - p[pitch];
+                const float mag = sqrtf(gx * gx + gy * gy);
+                const float ang = mod360f(atan2f(gy, gx) * B200_RAD2DEGF);
+                const float wgt = expf(weight_fac * (float)(dx * dx + dy * dy));
+                bin[u] = live ? (int)rintf(ang * (float)nb / 360.f) % nb : -1;
+                val[u] = wgt * mag;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                if (bin[u] >= 0) hist[bin[u]][lane] += (double)val[u];
         }
         __syncwarp();
         for (int b = lane; b < nb; b += 32) {
@@ -621,6 +638,91 @@ gather_kernel(const RawKeypoint *__restrict__ raw, const uint8_t *__restrict__ r
     }
 }
 
+// ---------------------------------------------------------------------------
+// Per-image ordering in shared memory (the common case: <= 4096 oriented keypoints per image).
+// bucket_kernel groups the raw keypoint indices by image; sort_image_kernel (one CTA per image)
+// loads the comparator keys of its segment into shared memory and runs a bitonic network on a
+// permutation of slots.  The comparator is the total order of KpLess (compare_keypoints,
+// sift_impl.py:299-311, then the scan-order key), so the result does not depend on the arbitrary
+// order in which the atomics filled the segment.  Larger images take the CUB merge sort below.
+// ---------------------------------------------------------------------------
+constexpr int kSortMaxPerImage = 4096;
+constexpr uint32_t kSortSentinel = 0xFFFFFFFFu;
+
+__global__ void __launch_bounds__(256)
+bucket_kernel(const RawKeypoint *__restrict__ raw, int n, const int *__restrict__ seg_off, int *__restrict__ cursor,
+              uint32_t *__restrict__ out_idx)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const int img = raw[i].img;
+    const int slot = atomicAdd(&cursor[img], 1);
+    out_idx[seg_off[img] + slot] = i;
+}
+
+struct SortKeys {
+    float *x, *y, *size, *angle, *resp;
+    unsigned long long *order;
+    __device__ __forceinline__ bool less(uint32_t a, uint32_t b, int scan_order) const
+    {
+        if (a == kSortSentinel) return false;
+        if (b == kSortSentinel) return true;
+        if (!scan_order) {
+            if (x[a] != x[b]) return x[a] < x[b];
+            if (y[a] != y[b]) return y[a] < y[b];
+            if (size[a] != size[b]) return size[a] > size[b];
+            if (angle[a] != angle[b]) return angle[a] < angle[b];
+            if (resp[a] != resp[b]) return resp[a] > resp[b];
+        }
+        return order[a] < order[b];
+    }
+};
+
+__global__ void __launch_bounds__(1024)
+sort_image_kernel(const RawKeypoint *__restrict__ raw, const int *__restrict__ seg_off,
+                  const uint32_t *__restrict__ idx_in, uint32_t *__restrict__ idx_out, int scan_order, int P_max)
+{
+    extern __shared__ __align__(16) unsigned char ssm[];
+    SortKeys K;
+    K.order = reinterpret_cast<unsigned long long *>(ssm);
+    K.x = reinterpret_cast<float *>(K.order + P_max);
+    K.y = K.x + P_max; K.size = K.y + P_max; K.angle = K.size + P_max; K.resp = K.angle + P_max;
+    uint32_t *rid = reinterpret_cast<uint32_t *>(K.resp + P_max);
+    uint32_t *perm = rid + P_max;
+    const int base = seg_off[blockIdx.x], n = seg_off[blockIdx.x + 1] - base;
+    if (n <= 0) return;
+    int P = 2;
+    while (P < n) P <<= 1;
+    for (int s = threadIdx.x; s < P; s += 1024) {
+        if (s < n) {
+            const uint32_t r = idx_in[base + s];
+            const RawKeypoint k = raw[r];
+            K.x[s] = k.x; K.y[s] = k.y; K.size[s] = k.size; K.angle[s] = k.angle; K.resp[s] = k.response;
+            K.order[s] = k.order;
+            rid[s] = r;
+            perm[s] = s;
+        } else {
+            perm[s] = kSortSentinel;
+        }
+    }
+    __syncthreads();
+    for (int k = 2; k <= P; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (P >> 1); t += 1024) {
+                const int i1 = 2 * t - (t & (j - 1));
+                const int i2 = i1 + j;
+                const uint32_t a = perm[i1], b = perm[i2];
+                const bool up = (i1 & k) == 0;
+                // ascending block: want perm[i1] <= perm[i2]
+                const bool swap = up ? K.less(b, a, scan_order) : K.less(a, b, scan_order);
+                if (swap) { perm[i1] = b; perm[i2] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int s = threadIdx.x; s < n; s += 1024) idx_out[base + s] = rid[perm[s]];
+}
+
 static int ensure_sparse(b200sift_ctx *c, int cand_cap, int loc_cap, int raw_cap)
 {
     size_t cap;
@@ -672,7 +774,7 @@ int run_detect(b200sift_ctx *c, const b200sift_params &p, int /*want_scan_order*
     B200_ARG(p.ori_bins >= 4 && p.ori_bins <= kOriMaxBins);
     B200_ARG(p.max_iter >= 1);
     B200_ARG(py.h[0] < 32768 && py.w[0] < 32768 && py.n_img < 65536);
-    const PyrView v = make_view(py);
+    const PyrView v = make_view(c);
     const DetectParams dp = make_detect_params(p);
     B200_CHECK(ensure_counters(c, py.n_img));
     const size_t px = (size_t)py.n_img * py.h[0] * py.w[0];
@@ -734,7 +836,7 @@ int run_describe(b200sift_ctx *c, const b200sift_params &p, const RawKeypoint *d
 {
     if (n <= 0) return 0;
     B200_ARG(p.window_width == 4 && p.desc_bins == 8);
-    const PyrView v = make_view(c->pyr);
+    const PyrView v = make_view(c);
     const DetectParams dp = make_detect_params(p);
     const size_t smem = (size_t)kDescWarps * kDescSmemPerWarp;
     static bool attr = false;
@@ -744,7 +846,10 @@ int run_describe(b200sift_ctx *c, const b200sift_params &p, const RawKeypoint *d
     }
     int blocks = (n + kDescWarps - 1) / kDescWarps;
     if (blocks > c->sm_count * 3 * 4) blocks = c->sm_count * 3 * 4;
-    describe_kernel<<<blocks, kDescWarps * 32, smem, c->stream>>>(v, dp, d_raw, n, converted, d_out);
+    B200_CHECK(ensure_counters(c, c->pyr.n_img > 0 ? c->pyr.n_img : 1));
+    B200_CUDA(cudaMemsetAsync(c->d_counters + CNT_WORK_DESC, 0, sizeof(int32_t), c->stream));
+    describe_kernel<<<blocks, kDescWarps * 32, smem, c->stream>>>(v, dp, d_raw, n, converted, d_out,
+                                                                  c->d_counters + CNT_WORK_DESC);
     c->launches++;
     B200_CUDA(cudaGetLastError());
     return 0;
@@ -758,12 +863,27 @@ int run_sort_gather(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int d
     c->img_off.assign(n_img + 1, 0);
     if (n_raw <= 0) return 0;
     const int blocks = (n_raw + 255) / 256;
-    iota_kernel<<<blocks, 256, 0, c->stream>>>(c->d_sort_idx, n_raw);
-    c->launches++;
+    // per-image raw counts (known on the host since the read-back that ended run_detect)
+    std::vector<int> &seg = c->h_seg;
+    seg.assign(n_img + 1, 0);
+    int max_per = 0;
+    bool have_counts = false;
+    if (n_img == 1) {
+        seg[1] = n_raw;
+        max_per = n_raw;
+        have_counts = true;
+    } else if ((int)c->stat_raw.size() == n_img) {
+        for (int i = 0; i < n_img; ++i) {
+            seg[i + 1] = seg[i] + c->stat_raw[i];
+            if (c->stat_raw[i] > max_per) max_per = c->stat_raw[i];
+        }
+        have_counts = (seg[n_img] == n_raw);
+    }
+    // temp storage for the scan (and the merge-sort fall-back)
+    size_t tmp = 0, tmp2 = 0;
     KpLess less{c->d_raw, scan_order};
-    size_t tmp = 0;
-    B200_CUDA(cub::DeviceMergeSort::StableSortKeys(nullptr, tmp, c->d_sort_idx, n_raw, less, c->stream));
-    size_t tmp2 = 0;
+    const bool fast = have_counts && max_per <= kSortMaxPerImage;
+    if (!fast) B200_CUDA(cub::DeviceMergeSort::StableSortKeys(nullptr, tmp, c->d_sort_idx, n_raw, less, c->stream));
     B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, c->d_keep, c->d_pos, n_raw, c->stream));
     if (tmp2 > tmp) tmp = tmp2;
     if (tmp > c->cub_tmp_cap) {
@@ -773,8 +893,30 @@ int run_sort_gather(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int d
         c->cub_tmp_cap = tmp + 1024;
     }
     size_t t1 = c->cub_tmp_cap;
-    B200_CUDA(cub::DeviceMergeSort::StableSortKeys(c->d_cub_tmp, t1, c->d_sort_idx, n_raw, less, c->stream));
-    c->launches += 2;
+    if (fast) {
+        size_t cap = c->seg_cap;
+        B200_CHECK(ensure(&c->d_seg, &cap, (size_t)2 * (n_img + 1)));
+        c->seg_cap = cap;
+        int *d_off = c->d_seg, *d_cur = c->d_seg + (n_img + 1);
+        B200_CUDA(cudaMemcpyAsync(d_off, seg.data(), sizeof(int) * (n_img + 1), cudaMemcpyHostToDevice, c->stream));
+        B200_CUDA(cudaMemsetAsync(d_cur, 0, sizeof(int) * (n_img + 1), c->stream));
+        int P = 2;
+        while (P < max_per) P <<= 1;
+        const size_t smem = (size_t)P * (8 + 5 * 4 + 4 + 4);
+        static size_t attr_smem = 48 * 1024;
+        if (smem > attr_smem) {
+            B200_CUDA(cudaFuncSetAttribute(sort_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_smem = smem;
+        }
+        // d_pos doubles as the bucketed (unsorted) index list; it is rewritten by the scan afterwards
+        bucket_kernel<<<blocks, 256, 0, c->stream>>>(c->d_raw, n_raw, d_off, d_cur, c->d_pos);
+        sort_image_kernel<<<n_img, 1024, smem, c->stream>>>(c->d_raw, d_off, c->d_pos, c->d_sort_idx, scan_order, P);
+        c->launches += 2;
+    } else {
+        iota_kernel<<<blocks, 256, 0, c->stream>>>(c->d_sort_idx, n_raw);
+        B200_CUDA(cub::DeviceMergeSort::StableSortKeys(c->d_cub_tmp, t1, c->d_sort_idx, n_raw, less, c->stream));
+        c->launches += 3;
+    }
     zero_out_counts_kernel<<<(n_img + 255) / 256, 256, 0, c->stream>>>(c->d_counters, n_img);
     flag_kernel<<<blocks, 256, 0, c->stream>>>(c->d_raw, c->d_sort_idx, n_raw, dedupe, c->d_keep);
     t1 = c->cub_tmp_cap;
