@@ -147,7 +147,8 @@ void b200sift_destroy(b200sift_ctx *c)
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->pyr.base, c->d_up, c->d_in, c->d_dog, c->d_cand, c->d_loc, c->d_raw, c->d_raw_desc,
                     c->d_sort_idx, c->d_keep, c->d_pos, c->d_cub_tmp, c->d_kps, c->d_desc, c->d_counters,
-                    c->d_mA, c->d_mB, c->d_mout, c->d_nrmB, c->d_misc, c->d_pair, c->d_tc, c->d_tcsrc, c->d_seg};
+                    c->d_mA, c->d_mB, c->d_mout, c->d_nrmB, c->d_misc, c->d_pair, c->d_tc, c->d_tcsrc, c->d_seg, c->d_ptrs};
+    if (c->h_ptrs) cudaFreeHost(c->h_ptrs);
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->h_counters) cudaFreeHost(c->h_counters);
@@ -202,20 +203,32 @@ int b200sift_detect_describe(b200sift_ctx *c, const b200sift_params *params, int
     if (row_stride == 0) row_stride = min_stride;
     B200_ARG(row_stride >= min_stride);
 
-    // ---- stage the inputs (one dense block per image)
+    // ---- inputs: host images are staged into one dense block per image; device-resident images
+    // are read in place through a pointer table (no copies)
     const size_t img_bytes = ((min_stride * h) + 255) & ~(size_t)255;
     const uint8_t *d_in = nullptr;
+    const void *const *d_ptrs = nullptr;
     size_t in_row_stride = min_stride, in_img_stride = img_bytes;
-    {
+    for (int i = 0; i < n_images; ++i) B200_ARG(images[i] != nullptr);
+    if (on_device) {
+        if ((size_t)n_images > c->ptrs_cap) {
+            if (c->d_ptrs) cudaFree(c->d_ptrs);
+            if (c->h_ptrs) cudaFreeHost(c->h_ptrs);
+            c->ptrs_cap = (size_t)n_images + 64;
+            B200_CUDA(cudaMalloc((void **)&c->d_ptrs, c->ptrs_cap * sizeof(void *)));
+            B200_CUDA(cudaMallocHost((void **)&c->h_ptrs, c->ptrs_cap * sizeof(void *)));
+        }
+        for (int i = 0; i < n_images; ++i) c->h_ptrs[i] = const_cast<void *>(images[i]);
+        B200_CUDA(cudaMemcpyAsync(c->d_ptrs, c->h_ptrs, sizeof(void *) * n_images, cudaMemcpyHostToDevice, c->stream));
+        d_ptrs = c->d_ptrs;
+        in_row_stride = row_stride;
+    } else {
         size_t cap = c->in_cap;
         B200_CHECK(ensure(&c->d_in, &cap, img_bytes * n_images));
         c->in_cap = cap;
-        for (int i = 0; i < n_images; ++i) {
-            B200_ARG(images[i] != nullptr);
+        for (int i = 0; i < n_images; ++i)
             B200_CUDA(cudaMemcpy2DAsync(c->d_in + (size_t)i * img_bytes, min_stride, images[i], row_stride,
-                                        min_stride, h, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
-                                        c->stream));
-        }
+                                        min_stride, h, cudaMemcpyHostToDevice, c->stream));
         d_in = c->d_in;
     }
 
@@ -235,7 +248,7 @@ int b200sift_detect_describe(b200sift_ctx *c, const b200sift_params *params, int
     const double sigma_diff = sqrt(d2 > 0.01 ? d2 : 0.01);  // sift_impl.py:55
 
     Timer tm(c);
-    B200_CHECK(launch_gray_upsample(c, d_in, in_img_stride, in_row_stride, n_images, h, w, channels, dtype, c->d_up,
+    B200_CHECK(launch_gray_upsample(c, d_in, in_img_stride, d_ptrs, in_row_stride, n_images, h, w, channels, dtype, c->d_up,
                                     c->pyr.pitch[0]));
     B200_CHECK(base_blur(c, c->d_up, sigma_diff));
     B200_CHECK(build_octaves(c, sig));
@@ -281,6 +294,24 @@ int b200sift_get_keypoints(b200sift_ctx *c, int image, b200sift_keypoint *kps, f
         B200_CUDA(cudaStreamSynchronize(c->stream));
         for (size_t i = 0; i < (size_t)n * 128; ++i) desc_f32[i] = (float)tmp[i];
     }
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int b200sift_get_all_keypoints(b200sift_ctx *c, b200sift_keypoint *kps, uint8_t *desc_u8)
+{
+    B200_ARG(c != nullptr);
+    if (!c->have_results) {
+        set_error("get_all_keypoints before a successful detect_describe");
+        return B200SIFT_ESTATE;
+    }
+    const int n = c->img_off.back();
+    if (n == 0) return 0;
+    if (kps)
+        B200_CUDA(cudaMemcpyAsync(kps, c->d_kps, sizeof(b200sift_keypoint) * (size_t)n, cudaMemcpyDeviceToHost,
+                                  c->stream));
+    if (desc_u8)
+        B200_CUDA(cudaMemcpyAsync(desc_u8, c->d_desc, (size_t)n * 128, cudaMemcpyDeviceToHost, c->stream));
     B200_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -535,7 +566,7 @@ int b200sift_base_image(b200sift_ctx *c, const float *image, int h, int w, doubl
     c->up_cap = cap;
     B200_CUDA(cudaMemcpyAsync(c->d_in, image, (size_t)h * w * 4, cudaMemcpyHostToDevice, c->stream));
     float *d_up = c->d_up, *d_dst = c->d_up + (size_t)H * pitch;
-    B200_CHECK(launch_gray_upsample(c, c->d_in, 0, (size_t)w * 4, 1, h, w, 1, B200SIFT_F32, d_up, pitch));
+    B200_CHECK(launch_gray_upsample(c, c->d_in, 0, nullptr, (size_t)w * 4, 1, h, w, 1, B200SIFT_F32, d_up, pitch));
     const double d2 = sigma * sigma - (2 * assumed_blur) * (2 * assumed_blur);
     B200_CHECK(launch_blur(c, d_up, d_dst, 1, H, W, pitch, (size_t)H * pitch, sqrt(d2 > 0.01 ? d2 : 0.01), nullptr,
                            0, 0, 0, 0));

@@ -118,6 +118,7 @@ struct b200sift_ctx {
     b200::Pyramid pyr;
     float *d_up = nullptr;  size_t up_cap = 0;     // upsampled (pre-blur) base, [img][2h][pitch0]
     uint8_t *d_in = nullptr; size_t in_cap = 0;    // uploaded input images
+    void **d_ptrs = nullptr, **h_ptrs = nullptr; size_t ptrs_cap = 0;  // pointer table of device-resident inputs
     float *d_dog = nullptr; size_t dog_cap = 0;    // materialised DoG (stage API only)
 
     // sparse stage
@@ -172,8 +173,9 @@ int ensure(T **p, size_t *cap, size_t need)
 
 // pyramid.cu
 int pyramid_layout(b200sift_ctx *c, int n_img, int h0, int w0, int n_oct, int n_layers);
-int launch_gray_upsample(b200sift_ctx *c, const void *d_in, size_t img_stride_bytes, size_t row_stride,
-                         int n_img, int h, int w, int channels, int dtype, float *d_out, int out_pitch);
+int launch_gray_upsample(b200sift_ctx *c, const void *d_in, size_t img_stride_bytes, const void *const *d_ptrs,
+                         size_t row_stride, int n_img, int h, int w, int channels, int dtype, float *d_out,
+                         int out_pitch);
 int launch_blur(b200sift_ctx *c, const float *src, float *dst, int n_img, int h, int w, int pitch,
                 size_t img_stride, double sigma, float *dst2, int h2, int w2, int pitch2,
                 size_t img_stride2);

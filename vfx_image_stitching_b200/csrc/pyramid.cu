@@ -95,13 +95,15 @@ __device__ __forceinline__ float load_grey(const uint8_t *img, size_t row_stride
 }
 
 __global__ void __launch_bounds__(256) gray_upsample_kernel(const uint8_t *__restrict__ in, size_t img_stride_bytes,
+                                                            const uint8_t *const *__restrict__ ptrs,
                                                             size_t row_stride, int h, int w, int channels, int dtype,
                                                             float *__restrict__ out, int out_pitch)
 {
     const int X = blockIdx.x * 32 + (threadIdx.x & 31);
     const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
     if (X >= 2 * w || Y >= 2 * h) return;
-    const uint8_t *img = in + (size_t)blockIdx.z * img_stride_bytes;
+    // images either sit at a fixed stride behind `in` or are named one by one in `ptrs`
+    const uint8_t *img = ptrs ? ptrs[blockIdx.z] : in + (size_t)blockIdx.z * img_stride_bytes;
     int sx = (X & 1) ? (X >> 1) : (X >> 1) - 1;
     float fx = (X & 1) ? 0.25f : 0.75f;
     if (sx < 0) { sx = 0; fx = 0.f; }
@@ -122,12 +124,14 @@ __global__ void __launch_bounds__(256) gray_upsample_kernel(const uint8_t *__res
     out[(size_t)blockIdx.z * (size_t)(2 * h) * out_pitch + (size_t)Y * out_pitch + X] = v;
 }
 
-int launch_gray_upsample(b200sift_ctx *c, const void *d_in, size_t img_stride_bytes, size_t row_stride, int n_img,
-                         int h, int w, int channels, int dtype, float *d_out, int out_pitch)
+int launch_gray_upsample(b200sift_ctx *c, const void *d_in, size_t img_stride_bytes, const void *const *d_ptrs,
+                         size_t row_stride, int n_img, int h, int w, int channels, int dtype, float *d_out,
+                         int out_pitch)
 {
     dim3 grid((2 * w + 31) / 32, (2 * h + 7) / 8, n_img);
-    gray_upsample_kernel<<<grid, 256, 0, c->stream>>>((const uint8_t *)d_in, img_stride_bytes, row_stride, h, w,
-                                                      channels, dtype, d_out, out_pitch);
+    gray_upsample_kernel<<<grid, 256, 0, c->stream>>>((const uint8_t *)d_in, img_stride_bytes,
+                                                      (const uint8_t *const *)d_ptrs, row_stride, h, w, channels,
+                                                      dtype, d_out, out_pitch);
     c->launches++;
     B200_CUDA(cudaGetLastError());
     return 0;

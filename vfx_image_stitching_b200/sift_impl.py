@@ -127,17 +127,21 @@ def detect_and_describe_batch(images, sigma=1.6, num_intervals=3, assumed_blur=0
     return download_results(counts, ctx)
 
 
-def download_results(counts, ctx=None):
-    """(keypoints, uint8 descriptors) of every image of the last detect, copied to the host."""
+def download_results(counts, ctx=None, out=None):
+    """(keypoints, uint8 descriptors) of every image of the last detect, copied to the host in two
+    transfers.  `out` = optional (kps, desc) host arrays to fill (e.g. views of pinned memory)."""
     ctx = ctx or default_context()
-    out = []
-    for i, n in enumerate(counts):
-        kps = np.zeros(int(n), KP_DTYPE)
-        desc = np.zeros((int(n), 128), np.uint8)
-        if n:
-            check(ctx.lib.b200sift_get_keypoints(ctx.handle, i, ptr(kps), None, ptr(desc)))
-        out.append((kps, desc))
-    return out
+    counts = np.asarray(counts, np.int64)
+    total = int(counts.sum())
+    if out is None:
+        kps = np.empty(total, KP_DTYPE)
+        desc = np.empty((total, 128), np.uint8)
+    else:
+        kps, desc = out[0][:total], out[1][:total]
+    if total:
+        check(ctx.lib.b200sift_get_all_keypoints(ctx.handle, ptr(kps), ptr(desc)))
+    off = np.concatenate([[0], np.cumsum(counts)])
+    return [(kps[off[i]:off[i + 1]], desc[off[i]:off[i + 1]]) for i in range(len(counts))]
 
 
 def _detect_device_tensors(images, sigma, num_intervals, assumed_blur, image_border_width, ctx, download):
