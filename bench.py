@@ -200,13 +200,14 @@ def main():
     def step_resident():
         """inputs in HBM; per-pair results stay on the device except counts / the voted shift."""
         if world == 1:
-            return iss.panorama_shifts(resident, ctx=ctx, return_details=True)
+            return iss.panorama_shifts(resident, ctx=ctx)          # [(dx, dy)] * 17, like the reference loop
         return panorama.sharded_panorama_shifts(resident, backend, dist=dist, device=dev)
 
     def step_e2e():
         """host images in, host keypoints + descriptors + shifts out."""
         if world == 1:
-            shifts, counts, det = iss.panorama_shifts(pinned_np, ctx=ctx, return_details=True)
+            counts = sift_impl.detect_and_describe_batch(pinned_np, ctx=ctx, download=False)
+            shifts = iss.match_pairs([(i, i + 1) for i in range(n - 1)], 3, 25000, ctx)[0]
             res = sift_impl.download_results(counts, ctx)
             return shifts, counts, res
         shifts, counts = panorama.sharded_panorama_shifts(pinned_np, backend, dist=dist, device=dev)
@@ -244,7 +245,7 @@ def main():
     ms_e2e, wall_e2e, out_e2e, _ = timed(step_e2e, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
 
-    counts = np.asarray(out_dev[1])
+    counts = np.asarray(out_e2e[1])
     desc_pairs = float(sum(int(counts[i]) * int(counts[i + 1]) for i in range(n - 1)))
     h2d = sum(int(t.numel()) for t in pinned[lo:hi])
     d2h = int(sum(int(c) for c in counts[lo:hi])) * (24 + 128) + (n - 1) * 16

@@ -4,6 +4,7 @@
 #include <math.h>
 #include <algorithm>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -29,6 +30,37 @@ struct Timer {
         cudaEventRecord(c->ev1, c->stream);
         cudaEventSynchronize(c->ev1);
         cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
+    }
+};
+
+// B200SIFT_TRACE=1: device time between phase boundaries of detect_describe (CUDA events on the
+// context stream, so host gaps inside a phase count towards it), printed to stderr.
+struct Trace {
+    bool on;
+    std::vector<cudaEvent_t> ev;
+    std::vector<const char *> name;
+    Trace() : on(getenv("B200SIFT_TRACE") != nullptr) {}
+    void mark(b200sift_ctx *c, const char *n)
+    {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, c->stream);
+        ev.push_back(e);
+        name.push_back(n);
+    }
+    void report()
+    {
+        if (!on || ev.empty()) return;
+        cudaEventSynchronize(ev.back());
+        for (size_t i = 1; i < ev.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ev[i - 1], ev[i]);
+            fprintf(stderr, "[b200sift trace] %-22s %8.1f us\n", name[i], ms * 1e3);
+        }
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        ev.clear();
+        name.clear();
     }
 };
 
@@ -248,16 +280,24 @@ int b200sift_detect_describe(b200sift_ctx *c, const b200sift_params *params, int
     const double sigma_diff = sqrt(d2 > 0.01 ? d2 : 0.01);  // sift_impl.py:55
 
     Timer tm(c);
+    static Trace tr;
+    tr.mark(c, "start");
     B200_CHECK(launch_gray_upsample(c, d_in, in_img_stride, d_ptrs, in_row_stride, n_images, h, w, channels, dtype, c->d_up,
                                     c->pyr.pitch[0]));
     B200_CHECK(base_blur(c, c->d_up, sigma_diff));
+    tr.mark(c, "upsample+base blur");
     B200_CHECK(build_octaves(c, sig));
+    tr.mark(c, "octaves (blur)");
     B200_CHECK(run_detect(c, P, 0));
+    tr.mark(c, "extrema+refine+orient");
     fill_stats(c);
     const int n_raw = c->h_counters[CNT_RAW];
     B200_CHECK(run_describe(c, P, c->d_raw, n_raw, 0, c->d_raw_desc));
+    tr.mark(c, "describe");
     B200_CHECK(run_sort_gather(c, n_raw, n_images, 0, 1, 1, 1));
+    tr.mark(c, "sort+gather");
     tm.stop();
+    tr.report();
     c->n_img_last = n_images;
     c->have_results = true;
     if (n_keypoints)

@@ -146,10 +146,12 @@ struct b200sift_ctx {
     void *d_misc = nullptr; size_t misc_cap = 0;
     uint8_t *d_pair = nullptr; size_t pair_cap = 0;   // batched pair matching scratch
     uint8_t *d_tc = nullptr; size_t tc_cap = 0;       // tensor-core matcher: packed descriptors + norms
+    std::vector<unsigned char> h_tc_tables;           // host copies of its small tables (kept alive for async copies)
     uint8_t *d_tcsrc = nullptr; size_t tcsrc_cap = 0; // generic match(): A and B side by side
     b200::PairResult *d_pair_res = nullptr; int32_t *d_pair_ia = nullptr, *d_pair_ib = nullptr;
     float *d_pair_xy = nullptr; int pair_rows_max = 0, pair_n = 0;
     std::vector<int> pair_counts;
+    std::vector<b200::PairDesc> h_pair_desc;
 };
 
 namespace b200 {

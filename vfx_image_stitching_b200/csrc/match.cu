@@ -286,7 +286,8 @@ pair_finalize_kernel(const PairDesc *__restrict__ pd, const int32_t *__restrict_
 int run_match_pairs(b200sift_ctx *c, int n_pairs, const int *h_pairs, int thresh, double vote_thr)
 {
     const int n_img = c->n_img_last;
-    std::vector<PairDesc> h_pd(n_pairs);
+    std::vector<PairDesc> &h_pd = c->h_pair_desc;  // read by an asynchronous copy below
+    h_pd.assign(n_pairs, PairDesc{0, 0, 0, 0});
     int rows_max = 1, nb_max = 0;
     for (int p = 0; p < n_pairs; ++p) {
         const int a = h_pairs[2 * p], b = h_pairs[2 * p + 1];

@@ -31,6 +31,7 @@
 // tiles t+2.. (ring).  K = 128 is only four MMA K-steps, so the kernel is epilogue-issue bound by
 // design: see DESIGN.md for the roofline arithmetic.
 #include <limits.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace b200 {
@@ -343,9 +344,12 @@ int run_match_tc(b200sift_ctx *c, const uint8_t *d_src, int n_imgs, const int *h
     int32_t *nrm = reinterpret_cast<int32_t *>(packed + (size_t)total * 128);
     PackImg *d_imgs = reinterpret_cast<PackImg *>(nrm + total);
     TcPair *d_tp = reinterpret_cast<TcPair *>(d_imgs + imgs.size());
-    // pageable -> device copies of small tables: stage through the stream in order
-    B200_CUDA(cudaMemcpyAsync(d_imgs, imgs.data(), imgs.size() * sizeof(PackImg), cudaMemcpyHostToDevice, c->stream));
-    B200_CUDA(cudaMemcpyAsync(d_tp, tp.data(), tp.size() * sizeof(TcPair), cudaMemcpyHostToDevice, c->stream));
+    // the small host tables must outlive the asynchronous copies: keep them in the context
+    c->h_tc_tables.resize(imgs.size() * sizeof(PackImg) + tp.size() * sizeof(TcPair));
+    memcpy(c->h_tc_tables.data(), imgs.data(), imgs.size() * sizeof(PackImg));
+    memcpy(c->h_tc_tables.data() + imgs.size() * sizeof(PackImg), tp.data(), tp.size() * sizeof(TcPair));
+    B200_CUDA(cudaMemcpyAsync(d_imgs, c->h_tc_tables.data(), c->h_tc_tables.size(), cudaMemcpyHostToDevice,
+                              c->stream));  // d_imgs and d_tp are adjacent
     if (max_pad > 0) {
         dim3 pg((max_pad * 8 + 255) / 256, n_imgs);
         pack_kernel<<<pg, 256, 0, c->stream>>>(d_src, d_imgs, packed, nrm);
@@ -368,8 +372,6 @@ int run_match_tc(b200sift_ctx *c, const uint8_t *d_src, int n_imgs, const int *h
                                                                             n_chunks_out, rows_max, d_part);
     c->launches++;
     B200_CUDA(cudaGetLastError());
-    // the host tables above are read by the async copies: they must outlive them
-    B200_CUDA(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
