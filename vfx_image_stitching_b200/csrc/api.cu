@@ -168,6 +168,10 @@ int b200sift_create(int device, b200sift_ctx **out)
     c->stream = c->own_stream;
     B200_CUDA(cudaEventCreate(&c->ev0));
     B200_CUDA(cudaEventCreate(&c->ev1));
+    B200_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    for (int o = 0; o < kMaxOctaves; ++o) B200_CUDA(cudaEventCreateWithFlags(&c->ev_oct[o], cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
     *out = c;
     return 0;
 }
@@ -186,6 +190,11 @@ void b200sift_destroy(b200sift_ctx *c)
     if (c->h_counters) cudaFreeHost(c->h_counters);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    for (int o = 0; o < kMaxOctaves; ++o) cudaEventDestroy(c->ev_oct[o]);
+    cudaEventDestroy(c->ev_side);
+    cudaEventDestroy(c->ev_main);
+    cudaStreamSynchronize(c->side_stream);
+    cudaStreamDestroy(c->side_stream);
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -292,10 +301,11 @@ int b200sift_detect_describe(b200sift_ctx *c, const b200sift_params *params, int
     tr.mark(c, "extrema+refine+orient");
     fill_stats(c);
     const int n_raw = c->h_counters[CNT_RAW];
+    B200_CHECK(run_sort_async(c, n_raw, n_images, 0));          // side stream, overlaps the descriptors
     B200_CHECK(run_describe(c, P, c->d_raw, n_raw, 0, c->d_raw_desc));
-    tr.mark(c, "describe");
-    B200_CHECK(run_sort_gather(c, n_raw, n_images, 0, 1, 1, 1));
-    tr.mark(c, "sort+gather");
+    tr.mark(c, "describe (|| sort)");
+    B200_CHECK(run_gather(c, n_raw, n_images, 1, 1, 1));
+    tr.mark(c, "dedupe+gather");
     tm.stop();
     tr.report();
     c->n_img_last = n_images;

@@ -112,6 +112,11 @@ struct b200sift_ctx {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // second stream: the extrema scan of octave o overlaps the blurs of octaves > o, and the keypoint
+    // sort overlaps the descriptor kernel (dependencies by events, no host involvement)
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t ev_oct[b200::kMaxOctaves] = {}, ev_side = nullptr, ev_main = nullptr;
+    bool oct_events_valid = false;
     float last_ms = 0.f;
     long long launches = 0;
 
@@ -191,6 +196,8 @@ int run_detect(b200sift_ctx *c, const b200sift_params &p, int want_scan_order);
 int run_describe(b200sift_ctx *c, const b200sift_params &p, const RawKeypoint *d_raw, int n, int converted,
                  uint8_t *d_out);
 int run_sort_gather(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int dedupe, int convert, int with_desc);
+int run_sort_async(b200sift_ctx *c, int n_raw, int n_img, int scan_order);   // on the side stream
+int run_gather(b200sift_ctx *c, int n_raw, int n_img, int dedupe, int convert, int with_desc);
 int ensure_sparse_for(b200sift_ctx *c, int n_img, int n_raw);
 int launch_ransac(b200sift_ctx *c, const float *d_matches, int n, double thr, double *move, int32_t *best);
 int launch_cyl(b200sift_ctx *c, const uint8_t *d_src, int h, int w, int ch, double f, uint8_t *d_dst);

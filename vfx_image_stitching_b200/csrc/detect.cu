@@ -785,23 +785,32 @@ int run_detect(b200sift_ctx *c, const b200sift_params &p, int /*want_scan_order*
     const int n_cnt = CNT_HDR + py.n_img * CNT_PER_IMG;
     for (int attempt = 0; attempt < 4; ++attempt) {
         B200_CHECK(ensure_sparse(c, cand_cap, loc_cap, raw_cap));
-        B200_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(int32_t) * n_cnt, c->stream));
+        // First attempt after build_octaves: the scan of octave o runs on the side stream as soon as
+        // that octave's layers are complete (event), i.e. next to the blurs of the following octaves.
+        const bool overlap = (attempt == 0) && c->oct_events_valid;
+        c->oct_events_valid = false;
+        cudaStream_t es = overlap ? c->side_stream : c->stream;
+        B200_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(int32_t) * n_cnt, es));
         const size_t ex_smem = (size_t)(py.n_layers - 1) * (kExTW + 2) * (kExTH + 2) * sizeof(float);
         for (int o = 0; o < py.n_oct; ++o) {
             const int sh = py.h[o] - 2 * p.image_border_width, sw = py.w[o] - 2 * p.image_border_width;
             if (sh <= 0 || sw <= 0) continue;
+            if (overlap) B200_CUDA(cudaStreamWaitEvent(es, c->ev_oct[o], 0));
             if (p.num_intervals == 3 && sw >= 24) {
                 const int n_cg = (sw + 29) / 30, n_rs = (sh + kExSegRows - 1) / kExSegRows;
                 dim3 grid((n_cg * n_rs + 7) / 8, py.n_img);
-                extrema_rows_kernel<3><<<grid, 256, 0, c->stream>>>(v, o, p.image_border_width, dp.dog_thresh, n_cg,
-                                                                   n_rs, c->d_cand, c->cand_cap, c->d_counters);
+                extrema_rows_kernel<3><<<grid, 256, 0, es>>>(v, o, p.image_border_width, dp.dog_thresh, n_cg, n_rs,
+                                                            c->d_cand, c->cand_cap, c->d_counters);
             } else {
                 dim3 grid((sw + kExTW - 1) / kExTW, (sh + kExTH - 1) / kExTH, py.n_img);
-                extrema_kernel<<<grid, 256, ex_smem, c->stream>>>(v, o, p.image_border_width, p.num_intervals,
-                                                                  dp.dog_thresh, c->d_cand, c->cand_cap,
-                                                                  c->d_counters);
+                extrema_kernel<<<grid, 256, ex_smem, es>>>(v, o, p.image_border_width, p.num_intervals, dp.dog_thresh,
+                                                           c->d_cand, c->cand_cap, c->d_counters);
             }
             c->launches++;
+        }
+        if (overlap) {
+            B200_CUDA(cudaEventRecord(c->ev_side, es));
+            B200_CUDA(cudaStreamWaitEvent(c->stream, c->ev_side, 0));
         }
         B200_CUDA(cudaGetLastError());
         {
@@ -857,11 +866,16 @@ int run_describe(b200sift_ctx *c, const b200sift_params &p, const RawKeypoint *d
 
 // Sort the n raw keypoints (by image, then compare_keypoints or scan order),
 // optionally drop duplicates, convert and compact into c->d_kps / c->d_desc.
-int run_sort_gather(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int dedupe, int convert, int with_desc)
+// Ordering of the n raw keypoints (by image, then compare_keypoints or scan order) into
+// c->d_sort_idx, on the side stream; run_gather() joins it.
+int run_sort_async(b200sift_ctx *c, int n_raw, int n_img, int scan_order)
 {
     B200_CHECK(ensure_counters(c, n_img));
     c->img_off.assign(n_img + 1, 0);
     if (n_raw <= 0) return 0;
+    cudaStream_t ss = c->side_stream;
+    B200_CUDA(cudaEventRecord(c->ev_main, c->stream));       // everything queued so far (uploads, d_raw)
+    B200_CUDA(cudaStreamWaitEvent(ss, c->ev_main, 0));
     const int blocks = (n_raw + 255) / 256;
     // per-image raw counts (known on the host since the read-back that ended run_detect)
     std::vector<int> &seg = c->h_seg;
@@ -879,27 +893,27 @@ int run_sort_gather(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int d
         }
         have_counts = (seg[n_img] == n_raw);
     }
-    // temp storage for the scan (and the merge-sort fall-back)
+    // temp storage for the scan of run_gather (and the merge-sort fall-back)
     size_t tmp = 0, tmp2 = 0;
     KpLess less{c->d_raw, scan_order};
     const bool fast = have_counts && max_per <= kSortMaxPerImage;
-    if (!fast) B200_CUDA(cub::DeviceMergeSort::StableSortKeys(nullptr, tmp, c->d_sort_idx, n_raw, less, c->stream));
-    B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, c->d_keep, c->d_pos, n_raw, c->stream));
+    if (!fast) B200_CUDA(cub::DeviceMergeSort::StableSortKeys(nullptr, tmp, c->d_sort_idx, n_raw, less, ss));
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, c->d_keep, c->d_pos, n_raw, ss));
     if (tmp2 > tmp) tmp = tmp2;
     if (tmp > c->cub_tmp_cap) {
+        B200_CUDA(cudaStreamSynchronize(c->stream));
         if (c->d_cub_tmp) cudaFree(c->d_cub_tmp);
         c->d_cub_tmp = nullptr;
         B200_CUDA(cudaMalloc(&c->d_cub_tmp, tmp + 1024));
         c->cub_tmp_cap = tmp + 1024;
     }
-    size_t t1 = c->cub_tmp_cap;
     if (fast) {
         size_t cap = c->seg_cap;
         B200_CHECK(ensure(&c->d_seg, &cap, (size_t)2 * (n_img + 1)));
         c->seg_cap = cap;
         int *d_off = c->d_seg, *d_cur = c->d_seg + (n_img + 1);
-        B200_CUDA(cudaMemcpyAsync(d_off, seg.data(), sizeof(int) * (n_img + 1), cudaMemcpyHostToDevice, c->stream));
-        B200_CUDA(cudaMemsetAsync(d_cur, 0, sizeof(int) * (n_img + 1), c->stream));
+        B200_CUDA(cudaMemcpyAsync(d_off, seg.data(), sizeof(int) * (n_img + 1), cudaMemcpyHostToDevice, ss));
+        B200_CUDA(cudaMemsetAsync(d_cur, 0, sizeof(int) * (n_img + 1), ss));
         int P = 2;
         while (P < max_per) P <<= 1;
         const size_t smem = (size_t)P * (8 + 5 * 4 + 4 + 4);
@@ -908,18 +922,30 @@ int run_sort_gather(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int d
             B200_CUDA(cudaFuncSetAttribute(sort_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_smem = smem;
         }
-        // d_pos doubles as the bucketed (unsorted) index list; it is rewritten by the scan afterwards
-        bucket_kernel<<<blocks, 256, 0, c->stream>>>(c->d_raw, n_raw, d_off, d_cur, c->d_pos);
-        sort_image_kernel<<<n_img, 1024, smem, c->stream>>>(c->d_raw, d_off, c->d_pos, c->d_sort_idx, scan_order, P);
+        // d_pos doubles as the bucketed (unsorted) index list; run_gather's scan rewrites it afterwards
+        bucket_kernel<<<blocks, 256, 0, ss>>>(c->d_raw, n_raw, d_off, d_cur, c->d_pos);
+        sort_image_kernel<<<n_img, 1024, smem, ss>>>(c->d_raw, d_off, c->d_pos, c->d_sort_idx, scan_order, P);
         c->launches += 2;
     } else {
-        iota_kernel<<<blocks, 256, 0, c->stream>>>(c->d_sort_idx, n_raw);
-        B200_CUDA(cub::DeviceMergeSort::StableSortKeys(c->d_cub_tmp, t1, c->d_sort_idx, n_raw, less, c->stream));
+        size_t t1 = c->cub_tmp_cap;
+        iota_kernel<<<blocks, 256, 0, ss>>>(c->d_sort_idx, n_raw);
+        B200_CUDA(cub::DeviceMergeSort::StableSortKeys(c->d_cub_tmp, t1, c->d_sort_idx, n_raw, less, ss));
         c->launches += 3;
     }
+    B200_CUDA(cudaGetLastError());
+    B200_CUDA(cudaEventRecord(c->ev_side, ss));
+    return 0;
+}
+
+// Join the sort, optionally drop duplicates, convert and compact into c->d_kps / c->d_desc.
+int run_gather(b200sift_ctx *c, int n_raw, int n_img, int dedupe, int convert, int with_desc)
+{
+    if (n_raw <= 0) return 0;
+    B200_CUDA(cudaStreamWaitEvent(c->stream, c->ev_side, 0));
+    const int blocks = (n_raw + 255) / 256;
     zero_out_counts_kernel<<<(n_img + 255) / 256, 256, 0, c->stream>>>(c->d_counters, n_img);
     flag_kernel<<<blocks, 256, 0, c->stream>>>(c->d_raw, c->d_sort_idx, n_raw, dedupe, c->d_keep);
-    t1 = c->cub_tmp_cap;
+    size_t t1 = c->cub_tmp_cap;
     B200_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub_tmp, t1, c->d_keep, c->d_pos, n_raw, c->stream));
     gather_kernel<<<(n_raw * 8 + 255) / 256, 256, 0, c->stream>>>(c->d_raw, with_desc ? c->d_raw_desc : nullptr,
                                                                   c->d_sort_idx, c->d_keep, c->d_pos, n_raw, convert,
@@ -932,6 +958,12 @@ int run_sort_gather(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int d
     B200_CUDA(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < n_img; ++i) c->img_off[i + 1] = c->img_off[i] + c->h_counters[CNT_HDR + i * CNT_PER_IMG + 3];
     return 0;
+}
+
+int run_sort_gather(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int dedupe, int convert, int with_desc)
+{
+    B200_CHECK(run_sort_async(c, n_raw, n_img, scan_order));
+    return run_gather(c, n_raw, n_img, dedupe, convert, with_desc);
 }
 
 int ensure_sparse_for(b200sift_ctx *c, int n_img, int n_raw)

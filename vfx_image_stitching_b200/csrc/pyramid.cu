@@ -270,6 +270,7 @@ int pyramid_layout(b200sift_ctx *c, int n_img, int h0, int w0, int n_oct, int n_
     B200_ARG(n_oct >= 1 && n_oct <= kMaxOctaves);
     B200_ARG(n_layers >= 4 && n_layers <= kMaxLayers);
     Pyramid &p = c->pyr;
+    c->oct_events_valid = false;
     p.n_img = n_img;
     p.n_oct = n_oct;
     p.n_layers = n_layers;
@@ -323,7 +324,9 @@ int build_octaves(b200sift_ctx *c, const double *sigmas)
             B200_CHECK(launch_blur_set(c, p.layer(o, l - 1), p.layer(o, l), p.n_img, p.h[o], p.w[o], p.pitch[o],
                                        p.img_stride(o), R[l], l, dst2, h2, w2, pitch2, is2));
         }
+        B200_CUDA(cudaEventRecord(c->ev_oct[o], c->stream));  // all layers of octave o are complete
     }
+    c->oct_events_valid = true;
     return 0;
 }
 
