@@ -139,24 +139,20 @@ int launch_gray_upsample(b200sift_ctx *c, const void *d_in, size_t img_stride_by
 
 #include "blur_strip.cuh"
 
-// Generic tile kernel: any radius <= kMaxBlurRadius, any (tiny) image.
-// 32x32 output tile per CTA, halo tile in shared memory, same arithmetic.
-__global__ void __launch_bounds__(256)
-blur_tile_kernel(const float *__restrict__ src, float *__restrict__ dst, float *__restrict__ dst2, int h, int w,
-                 int pitch, size_t img_stride, int h2, int w2, int pitch2, size_t img_stride2, int R, int tapset)
+// Generic tile blur: any radius <= kMaxBlurRadius, any (tiny) image.  32x32 output tile, halo tile in
+// shared memory, same arithmetic as the strip kernel.  All 256 threads of the CTA call it together.
+__device__ __forceinline__ void blur_tile(const float *__restrict__ src, float *__restrict__ dst,
+                                          float *__restrict__ dst2, int h, int w, int pitch, int h2, int w2,
+                                          int pitch2, int R, int tapset, int x0, int y0, float *smem)
 {
     constexpr int T = 32;
-    extern __shared__ __align__(16) float smem[];
     const int IW = T + 2 * R;
     float *in_s = smem;            // [IW][IW]
     float *hs = smem + IW * IW;    // [IW][T]
-    const int x0 = blockIdx.x * T, y0 = blockIdx.y * T;
-    src += (size_t)blockIdx.z * img_stride;
-    dst += (size_t)blockIdx.z * img_stride;
-    if (dst2) dst2 += (size_t)blockIdx.z * img_stride2;
     for (int i = threadIdx.x; i < IW * IW; i += 256) {
         const int yy = i / IW, xx = i - yy * IW;
-        in_s[i] = src[(size_t)reflect101(y0 - R + yy, h) * pitch + reflect101(x0 - R + xx, w)];
+        // L2 load: in the tail kernel the source layer was written by other CTAs of this launch
+        in_s[i] = __ldcg(&src[(size_t)reflect101(y0 - R + yy, h) * pitch + reflect101(x0 - R + xx, w)]);
     }
     __syncthreads();
     const float *taps = c_taps[tapset];
@@ -178,6 +174,132 @@ blur_tile_kernel(const float *__restrict__ src, float *__restrict__ dst, float *
         dst[(size_t)y * pitch + x] = acc;
         if (dst2 && !((y | x) & 1) && (y >> 1) < h2 && (x >> 1) < w2)
             dst2[(size_t)(y >> 1) * pitch2 + (x >> 1)] = acc;
+    }
+    __syncthreads();  // the shared tiles may be refilled by the caller's next tile
+}
+
+__global__ void __launch_bounds__(256)
+blur_tile_kernel(const float *__restrict__ src, float *__restrict__ dst, float *__restrict__ dst2, int h, int w,
+                 int pitch, size_t img_stride, int h2, int w2, int pitch2, size_t img_stride2, int R, int tapset)
+{
+    extern __shared__ __align__(16) float smem[];
+    src += (size_t)blockIdx.z * img_stride;
+    dst += (size_t)blockIdx.z * img_stride;
+    if (dst2) dst2 += (size_t)blockIdx.z * img_stride2;
+    blur_tile(src, dst, dst2, h, w, pitch, h2, w2, pitch2, R, tapset, blockIdx.x * 32, blockIdx.y * 32, smem);
+}
+
+// ---------------------------------------------------------------------------
+// Pyramid tail: ALL layers of ALL small octaves (<= 128 px wide) in ONE launch, one CTA per image.
+// With one kernel per layer the small octaves are pure launch latency (30 dependent launches of a
+// few microseconds each for a 1024x768 base).  Here the whole octave image lives in shared memory:
+//   A[h][w+2Rm]   current layer with a reflected x-halo      (row pass reads contiguous spans)
+//   B[h+2Rm][w]   row-filtered layer with a reflected y-halo (column pass reads contiguous spans)
+// Each thread produces 4 adjacent outputs per pass from 4+2R shared-memory values; the column pass
+// writes the new layer to HBM, back into A for the next blur of the chain (sift_impl.py:90-92) and,
+// for layer n_layers-3, its [::2, ::2] decimation as layer 0 of the next octave (:95-96).
+// Same arithmetic as the strip kernel (k0*c + sum k[k]*(a[+k]+a[-k]), fmaf, BORDER_REFLECT_101).
+// ---------------------------------------------------------------------------
+struct TailArgs {
+    float *base;                 // pyramid allocation
+    size_t oct_off[kMaxOctaves]; // float offset of octave o
+    int h[kMaxOctaves], w[kMaxOctaves], pitch[kMaxOctaves];
+    int radius[kMaxLayers];      // per layer (tap set index = layer)
+    int n_img, n_oct, n_layers, o_tail, r_max;
+};
+constexpr int kTailThreads = 1024;
+
+__global__ void __launch_bounds__(kTailThreads) pyramid_tail_kernel(const __grid_constant__ TailArgs a)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int img = blockIdx.x, tid = threadIdx.x, Rm = a.r_max;
+    const int h0 = a.h[a.o_tail], w0 = a.w[a.o_tail];
+    float *A = smem;                        // [h][w + 2Rm], sized for the first tail octave
+    float *B = smem + h0 * (w0 + 2 * Rm);   // [h + 2Rm][w]
+    for (int o = a.o_tail; o < a.n_oct; ++o) {
+        const int h = a.h[o], w = a.w[o], pitch = a.pitch[o];
+        const size_t istride = (size_t)h * pitch;
+        const int pa = w + 2 * Rm;
+        // layer 0 of this octave -> A interior (written by the previous kernel, or by this CTA below)
+        {
+            const float *src = a.base + a.oct_off[o] + (size_t)img * istride;
+            for (int i = tid; i < h * w; i += kTailThreads) {
+                const int y = i / w, x = i - y * w;
+                A[y * pa + Rm + x] = __ldcg(&src[(size_t)y * pitch + x]);
+            }
+        }
+        __syncthreads();
+        for (int l = 1; l < a.n_layers; ++l) {
+            const int R = a.radius[l];
+            const float *taps = c_taps[l];
+            float *dst = a.base + a.oct_off[o] + ((size_t)l * a.n_img + img) * istride;
+            float *dst2 = nullptr;
+            int h2 = 0, w2 = 0, pitch2 = 0;
+            if (l == a.n_layers - 3 && o + 1 < a.n_oct) {
+                h2 = a.h[o + 1]; w2 = a.w[o + 1]; pitch2 = a.pitch[o + 1];
+                dst2 = a.base + a.oct_off[o + 1] + (size_t)img * ((size_t)h2 * pitch2);
+            }
+            // reflected x-halo of A
+            for (int i = tid; i < h * 2 * R; i += kTailThreads) {
+                const int y = i / (2 * R), k = i - y * (2 * R);
+                const int x = k < R ? k - R : w + (k - R);  // -R..-1, w..w+R-1
+                A[y * pa + Rm + x] = A[y * pa + Rm + reflect101(x, w)];
+            }
+            __syncthreads();
+            // row pass: 4 adjacent x per thread, A -> B interior rows
+            const int xb = (w + 3) / 4;
+            for (int i = tid; i < h * xb; i += kTailThreads) {
+                const int y = i / xb, x0 = (i - y * xb) * 4;
+                const float *p = A + y * pa + Rm + x0;
+                float acc[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] = taps[0] * p[j];
+                for (int k = 1; k <= R; ++k) {
+                    const float t = taps[k];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (x0 + j < w) acc[j] = fmaf(t, p[j + k] + p[j - k], acc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (x0 + j < w) B[(y + Rm) * w + x0 + j] = acc[j];
+            }
+            __syncthreads();
+            // reflected y-halo of B
+            for (int i = tid; i < 2 * R * w; i += kTailThreads) {
+                const int k = i / w, x = i - k * w;
+                const int y = k < R ? k - R : h + (k - R);
+                B[(y + Rm) * w + x] = B[(reflect101(y, h) + Rm) * w + x];
+            }
+            __syncthreads();
+            // column pass: 4 adjacent y per thread, B -> HBM layer l, A interior, decimated seed
+            const int yb = (h + 3) / 4;
+            for (int i = tid; i < yb * w; i += kTailThreads) {
+                const int yblk = i / w, x = i - yblk * w, y0 = yblk * 4;
+                const float *p = B + (y0 + Rm) * w + x;
+                float acc[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[j] = (y0 + j < h) ? taps[0] * p[j * w] : 0.f;
+                for (int k = 1; k <= R; ++k) {
+                    const float t = taps[k];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (y0 + j < h) acc[j] = fmaf(t, p[(j + k) * w] + p[(j - k) * w], acc[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int y = y0 + j;
+                    if (y < h) {
+                        A[y * pa + Rm + x] = acc[j];
+                        dst[(size_t)y * pitch + x] = acc[j];
+                        if (dst2 && !((y | x) & 1) && (y >> 1) < h2 && (x >> 1) < w2)
+                            dst2[(size_t)(y >> 1) * pitch2 + (x >> 1)] = acc[j];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        __threadfence_block();
     }
 }
 
@@ -309,7 +431,29 @@ int build_octaves(b200sift_ctx *c, const double *sigmas)
     Pyramid &p = c->pyr;
     int R[kMaxLayers];
     for (int l = 1; l < p.n_layers; ++l) B200_CHECK(upload_taps(c, l, sigmas[l], &R[l]));
-    for (int o = 0; o < p.n_oct; ++o) {
+    // octaves of <= 128 x 128 px go to the tail kernel (one launch, one CTA per image) when the
+    // image + halos fit in shared memory
+    int o_tail = p.n_oct;
+    for (int o = 1; o < p.n_oct; ++o)
+        if (p.w[o] <= 128 && p.h[o] <= 160) { o_tail = o; break; }
+    int max_r = 0;
+    size_t tail_smem = 0;
+    if (o_tail < p.n_oct) {
+        for (int l = 1; l < p.n_layers; ++l) max_r = R[l] > max_r ? R[l] : max_r;
+        const int h0 = p.h[o_tail], w0 = p.w[o_tail];
+        tail_smem = ((size_t)h0 * (w0 + 2 * max_r) + (size_t)(h0 + 2 * max_r) * w0) * sizeof(float);
+        if (tail_smem > 200 * 1024) {
+            o_tail = p.n_oct;
+        } else {
+            static size_t attr_smem = 48 * 1024;
+            if (tail_smem > attr_smem) {
+                B200_CUDA(cudaFuncSetAttribute(pyramid_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)tail_smem));
+                attr_smem = tail_smem;
+            }
+        }
+    }
+    for (int o = 0; o < o_tail; ++o) {
         for (int l = 1; l < p.n_layers; ++l) {
             float *dst2 = nullptr;
             int h2 = 0, w2 = 0, pitch2 = 0;
@@ -325,6 +469,20 @@ int build_octaves(b200sift_ctx *c, const double *sigmas)
                                        p.img_stride(o), R[l], l, dst2, h2, w2, pitch2, is2));
         }
         B200_CUDA(cudaEventRecord(c->ev_oct[o], c->stream));  // all layers of octave o are complete
+    }
+    if (o_tail < p.n_oct) {
+        TailArgs a;
+        a.base = p.base;
+        for (int o = 0; o < p.n_oct; ++o) {
+            a.oct_off[o] = p.oct_off[o];
+            a.h[o] = p.h[o]; a.w[o] = p.w[o]; a.pitch[o] = p.pitch[o];
+        }
+        for (int l = 0; l < kMaxLayers; ++l) a.radius[l] = (l >= 1 && l < p.n_layers) ? R[l] : 0;
+        a.n_img = p.n_img; a.n_oct = p.n_oct; a.n_layers = p.n_layers; a.o_tail = o_tail; a.r_max = max_r;
+        pyramid_tail_kernel<<<p.n_img, kTailThreads, tail_smem, c->stream>>>(a);
+        B200_CUDA(cudaGetLastError());
+        c->launches++;
+        for (int o = o_tail; o < p.n_oct; ++o) B200_CUDA(cudaEventRecord(c->ev_oct[o], c->stream));
     }
     c->oct_events_valid = true;
     return 0;
