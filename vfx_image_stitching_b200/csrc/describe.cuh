@@ -81,7 +81,21 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
         // atan2, exp, shared-memory read-modify-write) interleave and hide each other's latency;
         // with 16 KB of histogram per warp only 12 warps fit on an SM.
         const double inv_hw = 1.0 / hw;
-        auto scatter2 = [&](const int (&xs)[2], const int (&ys)[2], const bool (&live)[2]) {
+        // gather4: the four neighbours of a queued pixel (every queued pixel lies inside the clipped
+        // window, so the address is always valid).  Issued one batch AHEAD of scatter2: the L2
+        // latency of the gather (the shared-memory histograms leave almost no L1) is covered by the
+        // arithmetic of the previous batch instead of stalling the warp.
+        auto gather4 = [&](const int (&xs)[2], const int (&ys)[2], float (&g)[2][4]) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float *p = img + (size_t)(pty + ys[u]) * pitch + (ptx + xs[u]);
+                g[u][0] = __ldg(p + 1);
+                g[u][1] = __ldg(p - 1);
+                g[u][2] = __ldg(p - pitch);
+                g[u][3] = __ldg(p + pitch);
+            }
+        };
+        auto scatter2 = [&](const int (&xs)[2], const int (&ys)[2], const bool (&live)[2], const float (&g)[2][4]) {
             bool okc[2][4];
             float *cell[2][4];
             float mv[2][4], w0[2], w1[2];
@@ -93,12 +107,8 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
                 const double qr = r_rot * inv_hw, qc = c_rot * inv_hw;
                 const double r_bin = qr + 1.5, c_bin = qc + 1.5;
                 const bool in = live[u] && (r_bin > -1.0 && r_bin < 4.0 && c_bin > -1.0 && c_bin < 4.0);
-                const float *p = img + (size_t)(pty + (in ? ys[u] : 0)) * pitch + (ptx + (in ? xs[u] : 0));
-                float gx = 0.f, gy = 0.f;
-                if (in) {
-                    gx = p[1] - p[-1];
-                    gy = p[-pitch] - p[pitch];
-                }
+                const float gx = in ? g[u][0] - g[u][1] : 0.f;
+                const float gy = in ? g[u][2] - g[u][3] : 0.f;
                 const float mag = sqrtf(gx * gx + gy * gy);
                 const float orient = mod360f(atan2f(gy, gx) * B200_RAD2DEGF);
                 const float fqr = (float)qr, fqc = (float)qc;
@@ -153,6 +163,10 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
         const int total = (ok && nx > 0 && ny > 0) ? nx * ny : 0;
         int yy = lane / max(nx, 1), xx = lane - yy * max(nx, 1);
         int qn = 0;  // warp-uniform queue length
+        int px[2] = {0, 0}, py[2] = {0, 0};  // batch whose gather is in flight
+        float pg[2][4];
+        bool pending = false;                // warp-uniform
+        const bool all_live[2] = {true, true};
         for (int idx0 = 0; idx0 < total; idx0 += 32) {
             const int ys = rlo + yy - pty, xs = clo + xx - ptx;
             xx += 32;
@@ -171,18 +185,34 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
             if (qn >= 64) {
                 const int sx[2] = {qx[lane], qx[lane + 32]}, sy[2] = {qy[lane], qy[lane + 32]};
                 const int tx = qx[lane + 64], ty = qy[lane + 64];
-                const bool live[2] = {true, true};
                 __syncwarp();
-                scatter2(sx, sy, live);
                 qn -= 64;
                 if (lane < qn) { qx[lane] = tx; qy[lane] = ty; }
+                float ng[2][4];
+                gather4(sx, sy, ng);
+                if (pending) scatter2(px, py, all_live, pg);
+                pending = true;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    px[u] = sx[u]; py[u] = sy[u];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) pg[u][k] = ng[u][k];
+                }
                 __syncwarp();
             }
         }
-        if (qn > 0) {
-            const int sx[2] = {qx[lane], qx[lane + 32]}, sy[2] = {qy[lane], qy[lane + 32]};
+        {
+            // drain: gather of the last (partial) batch goes out before the pending one is evaluated
+            int sx[2] = {0, 0}, sy[2] = {0, 0};
             const bool live[2] = {lane < qn, lane + 32 < qn};
-            scatter2(sx, sy, live);
+            if (qn > 0) {  // dead lanes gather queue entry 0 (a valid address) and drop the result
+                sx[0] = qx[live[0] ? lane : 0]; sy[0] = qy[live[0] ? lane : 0];
+                sx[1] = qx[live[1] ? lane + 32 : 0]; sy[1] = qy[live[1] ? lane + 32 : 0];
+            }
+            float ng[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+            if (qn > 0) gather4(sx, sy, ng);
+            if (pending) scatter2(px, py, all_live, pg);
+            if (qn > 0) scatter2(sx, sy, live, ng);
         }
         __syncwarp();
 

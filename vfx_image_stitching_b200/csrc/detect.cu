@@ -252,8 +252,11 @@ __device__ void sym3_pinv_solve(const double H[3][3], const double g[3], double 
             v[i][j] = (i == j) ? 1.0 : 0.0;
         }
     for (int sweep = 0; sweep < 60; ++sweep) {
+        // converged once the off-diagonal part is far below one ulp of the diagonal (Jacobi
+        // converges quadratically, so this costs at most one sweep more than needed; waiting for
+        // an exact zero would spin through all 60 sweeps and stall the whole warp)
         const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[1][2]);
-        if (off == 0.0) break;
+        if (off <= 1e-25 * (fabs(a[0][0]) + fabs(a[1][1]) + fabs(a[2][2]))) break;
 #pragma unroll
         for (int p = 0; p < 2; ++p)
 #pragma unroll

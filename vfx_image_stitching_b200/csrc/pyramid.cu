@@ -209,13 +209,90 @@ struct TailArgs {
 };
 constexpr int kTailThreads = 1024;
 
+// One blur of the chain on the shared-memory resident octave: A (x-halo) -> B (y-halo) -> A, HBM.
+// R is a template parameter so that the tap loops unroll into straight LDS / FADD / FFMA runs.
+// Lanes past the right / bottom edge compute on whatever lies there (inside the allocation, see
+// tail_smem_bytes) and only the stores are predicated.
+template <int R>
+__device__ __forceinline__ void tail_layer(float *A, float *B, const float *__restrict__ taps, int h, int w, int Rm,
+                                           float *__restrict__ dst, int pitch, float *__restrict__ dst2, int h2,
+                                           int w2, int pitch2)
+{
+    const int tid = threadIdx.x, pa = w + 2 * Rm;
+    float t[R + 1];
+#pragma unroll
+    for (int k = 0; k <= R; ++k) t[k] = taps[k];
+    // reflected x-halo of A
+    for (int i = tid; i < h * 2 * R; i += kTailThreads) {
+        const int y = i / (2 * R), k = i - y * (2 * R);
+        const int x = k < R ? k - R : w + (k - R);  // -R..-1, w..w+R-1
+        A[y * pa + Rm + x] = A[y * pa + Rm + reflect101(x, w)];
+    }
+    __syncthreads();
+    // row pass: 4 adjacent x per thread, A -> B interior rows
+    const int xb = (w + 3) >> 2;
+    for (int i = tid; i < h * xb; i += kTailThreads) {
+        const int y = i / xb, x0 = (i - y * xb) * 4;
+        const float *p = A + y * pa + Rm + x0 - R;
+        float v[4 + 2 * R];
+#pragma unroll
+        for (int q = 0; q < 4 + 2 * R; ++q) v[q] = p[q];
+        float *o = B + (y + Rm) * w + x0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float acc = t[0] * v[j + R];
+#pragma unroll
+            for (int k = 1; k <= R; ++k) acc = fmaf(t[k], v[j + R + k] + v[j + R - k], acc);
+            if (x0 + j < w) o[j] = acc;
+        }
+    }
+    __syncthreads();
+    // reflected y-halo of B
+    for (int i = tid; i < 2 * R * w; i += kTailThreads) {
+        const int k = i / w, x = i - k * w;
+        const int y = k < R ? k - R : h + (k - R);
+        B[(y + Rm) * w + x] = B[(reflect101(y, h) + Rm) * w + x];
+    }
+    __syncthreads();
+    // column pass: 4 adjacent y per thread, B -> HBM layer, A interior, decimated seed
+    const int yb = (h + 3) >> 2;
+    for (int i = tid; i < yb * w; i += kTailThreads) {
+        const int yblk = i / w, x = i - yblk * w, y0 = yblk * 4;
+        const float *p = B + (y0 + Rm - R) * w + x;
+        float v[4 + 2 * R];
+#pragma unroll
+        for (int q = 0; q < 4 + 2 * R; ++q) v[q] = p[q * w];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float acc = t[0] * v[j + R];
+#pragma unroll
+            for (int k = 1; k <= R; ++k) acc = fmaf(t[k], v[j + R + k] + v[j + R - k], acc);
+            const int y = y0 + j;
+            if (y < h) {
+                A[y * pa + Rm + x] = acc;
+                dst[(size_t)y * pitch + x] = acc;
+                if (dst2 && !((y | x) & 1) && (y >> 1) < h2 && (x >> 1) < w2)
+                    dst2[(size_t)(y >> 1) * pitch2 + (x >> 1)] = acc;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// floats of shared memory for a first tail octave of h0 x w0: A, B and 3 rows of slack for the
+// unpredicated reads of tail_layer
+static size_t tail_smem_bytes(int h0, int w0, int r_max)
+{
+    return ((size_t)h0 * (w0 + 2 * r_max) + (size_t)(h0 + 2 * r_max + 3) * w0 + 8) * sizeof(float);
+}
+
 __global__ void __launch_bounds__(kTailThreads) pyramid_tail_kernel(const __grid_constant__ TailArgs a)
 {
     extern __shared__ __align__(16) float smem[];
     const int img = blockIdx.x, tid = threadIdx.x, Rm = a.r_max;
     const int h0 = a.h[a.o_tail], w0 = a.w[a.o_tail];
     float *A = smem;                        // [h][w + 2Rm], sized for the first tail octave
-    float *B = smem + h0 * (w0 + 2 * Rm);   // [h + 2Rm][w]
+    float *B = smem + h0 * (w0 + 2 * Rm);   // [h + 2Rm (+3)][w]
     for (int o = a.o_tail; o < a.n_oct; ++o) {
         const int h = a.h[o], w = a.w[o], pitch = a.pitch[o];
         const size_t istride = (size_t)h * pitch;
@@ -239,65 +316,15 @@ __global__ void __launch_bounds__(kTailThreads) pyramid_tail_kernel(const __grid
                 h2 = a.h[o + 1]; w2 = a.w[o + 1]; pitch2 = a.pitch[o + 1];
                 dst2 = a.base + a.oct_off[o + 1] + (size_t)img * ((size_t)h2 * pitch2);
             }
-            // reflected x-halo of A
-            for (int i = tid; i < h * 2 * R; i += kTailThreads) {
-                const int y = i / (2 * R), k = i - y * (2 * R);
-                const int x = k < R ? k - R : w + (k - R);  // -R..-1, w..w+R-1
-                A[y * pa + Rm + x] = A[y * pa + Rm + reflect101(x, w)];
+            switch (R) {
+#define B200_TAIL_CASE(RR) case RR: tail_layer<RR>(A, B, taps, h, w, Rm, dst, pitch, dst2, h2, w2, pitch2); break;
+                B200_TAIL_CASE(1) B200_TAIL_CASE(2) B200_TAIL_CASE(3) B200_TAIL_CASE(4) B200_TAIL_CASE(5)
+                B200_TAIL_CASE(6) B200_TAIL_CASE(7) B200_TAIL_CASE(8) B200_TAIL_CASE(9) B200_TAIL_CASE(10)
+                B200_TAIL_CASE(11) B200_TAIL_CASE(12) B200_TAIL_CASE(13) B200_TAIL_CASE(14) B200_TAIL_CASE(15)
+                B200_TAIL_CASE(16)
+#undef B200_TAIL_CASE
+            default: break;  // host never routes other radii here
             }
-            __syncthreads();
-            // row pass: 4 adjacent x per thread, A -> B interior rows
-            const int xb = (w + 3) / 4;
-            for (int i = tid; i < h * xb; i += kTailThreads) {
-                const int y = i / xb, x0 = (i - y * xb) * 4;
-                const float *p = A + y * pa + Rm + x0;
-                float acc[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[j] = taps[0] * p[j];
-                for (int k = 1; k <= R; ++k) {
-                    const float t = taps[k];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (x0 + j < w) acc[j] = fmaf(t, p[j + k] + p[j - k], acc[j]);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if (x0 + j < w) B[(y + Rm) * w + x0 + j] = acc[j];
-            }
-            __syncthreads();
-            // reflected y-halo of B
-            for (int i = tid; i < 2 * R * w; i += kTailThreads) {
-                const int k = i / w, x = i - k * w;
-                const int y = k < R ? k - R : h + (k - R);
-                B[(y + Rm) * w + x] = B[(reflect101(y, h) + Rm) * w + x];
-            }
-            __syncthreads();
-            // column pass: 4 adjacent y per thread, B -> HBM layer l, A interior, decimated seed
-            const int yb = (h + 3) / 4;
-            for (int i = tid; i < yb * w; i += kTailThreads) {
-                const int yblk = i / w, x = i - yblk * w, y0 = yblk * 4;
-                const float *p = B + (y0 + Rm) * w + x;
-                float acc[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[j] = (y0 + j < h) ? taps[0] * p[j * w] : 0.f;
-                for (int k = 1; k <= R; ++k) {
-                    const float t = taps[k];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        if (y0 + j < h) acc[j] = fmaf(t, p[(j + k) * w] + p[(j - k) * w], acc[j]);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int y = y0 + j;
-                    if (y < h) {
-                        A[y * pa + Rm + x] = acc[j];
-                        dst[(size_t)y * pitch + x] = acc[j];
-                        if (dst2 && !((y | x) & 1) && (y >> 1) < h2 && (x >> 1) < w2)
-                            dst2[(size_t)(y >> 1) * pitch2 + (x >> 1)] = acc[j];
-                    }
-                }
-            }
-            __syncthreads();
         }
         __threadfence_block();
     }
@@ -441,8 +468,8 @@ int build_octaves(b200sift_ctx *c, const double *sigmas)
     if (o_tail < p.n_oct) {
         for (int l = 1; l < p.n_layers; ++l) max_r = R[l] > max_r ? R[l] : max_r;
         const int h0 = p.h[o_tail], w0 = p.w[o_tail];
-        tail_smem = ((size_t)h0 * (w0 + 2 * max_r) + (size_t)(h0 + 2 * max_r) * w0) * sizeof(float);
-        if (tail_smem > 200 * 1024) {
+        tail_smem = tail_smem_bytes(h0, w0, max_r);
+        if (tail_smem > 200 * 1024 || max_r > 16) {
             o_tail = p.n_oct;
         } else {
             static size_t attr_smem = 48 * 1024;
