@@ -220,6 +220,17 @@ def test_batch_equals_single(si, golden):
         assert np.array_equal(batch[i][0], k) and np.array_equal(batch[i][1], d)
 
 
+def test_download_refuses_short_buffer(si, golden):
+    """get_all_keypoints copies every image of the batch: a buffer sized for fewer is an error,
+    not an overflow."""
+    g = golden('parrington')
+    counts = si.detect_and_describe_batch([g['gray'][0], g['gray'][1]], download=False)
+    with pytest.raises(RuntimeError):
+        si.download_results(counts[:1])
+    full = si.download_results(counts)
+    assert [len(k) for k, _ in full] == [int(c) for c in counts]
+
+
 def test_empty_and_tiny_images(si):
     kps, desc = si.compute_keypoints_and_descriptors(np.full((40, 48), 7, np.uint8))
     assert kps == [] and desc.shape == (0,) and desc.dtype == np.float32

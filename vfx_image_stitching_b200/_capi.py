@@ -49,7 +49,7 @@ PROTOTYPES = {
     'b200sift_sync': (_i, [_vp]),
     'b200sift_detect_describe': (_i, [_vp, C.POINTER(Params), _i, _pp, _i, _i, _i, _i, _sz, _i, _ip]),
     'b200sift_get_keypoints': (_i, [_vp, _i, _vp, _vp, _vp]),
-    'b200sift_get_all_keypoints': (_i, [_vp, _vp, _vp]),
+    'b200sift_get_all_keypoints': (_i, [_vp, _vp, _vp, C.c_int64]),
     'b200sift_get_stats': (_i, [_vp, _i, _ip, _ip, _ip]),
     'b200sift_device_results': (_i, [_vp, _i, _pp, _pp, _ip]),
     'b200sift_match': (_i, [_vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),

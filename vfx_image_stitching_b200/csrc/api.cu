@@ -169,6 +169,9 @@ int b200sift_create(int device, b200sift_ctx **out)
     B200_CUDA(cudaEventCreate(&c->ev0));
     B200_CUDA(cudaEventCreate(&c->ev1));
     B200_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaStreamCreateWithFlags(&c->blur_side_stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaEventCreateWithFlags(&c->ev_seed, cudaEventDisableTiming));
+    B200_CUDA(cudaEventCreateWithFlags(&c->ev_blur_side, cudaEventDisableTiming));
     for (int o = 0; o < kMaxOctaves; ++o) B200_CUDA(cudaEventCreateWithFlags(&c->ev_oct[o], cudaEventDisableTiming));
     B200_CUDA(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
     B200_CUDA(cudaEventCreateWithFlags(&c->ev_main, cudaEventDisableTiming));
@@ -195,6 +198,10 @@ void b200sift_destroy(b200sift_ctx *c)
     cudaEventDestroy(c->ev_main);
     cudaStreamSynchronize(c->side_stream);
     cudaStreamDestroy(c->side_stream);
+    cudaStreamSynchronize(c->blur_side_stream);
+    cudaStreamDestroy(c->blur_side_stream);
+    cudaEventDestroy(c->ev_seed);
+    cudaEventDestroy(c->ev_blur_side);
     cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -348,7 +355,7 @@ int b200sift_get_keypoints(b200sift_ctx *c, int image, b200sift_keypoint *kps, f
     return 0;
 }
 
-int b200sift_get_all_keypoints(b200sift_ctx *c, b200sift_keypoint *kps, uint8_t *desc_u8)
+int b200sift_get_all_keypoints(b200sift_ctx *c, b200sift_keypoint *kps, uint8_t *desc_u8, int64_t capacity)
 {
     B200_ARG(c != nullptr);
     if (!c->have_results) {
@@ -357,6 +364,10 @@ int b200sift_get_all_keypoints(b200sift_ctx *c, b200sift_keypoint *kps, uint8_t 
     }
     const int n = c->img_off.back();
     if (n == 0) return 0;
+    if ((int64_t)n > capacity) {
+        set_error("get_all_keypoints: capacity %lld < %d keypoints", (long long)capacity, n);
+        return B200SIFT_EARG;
+    }
     if (kps)
         B200_CUDA(cudaMemcpyAsync(kps, c->d_kps, sizeof(b200sift_keypoint) * (size_t)n, cudaMemcpyDeviceToHost,
                                   c->stream));

@@ -115,6 +115,9 @@ struct b200sift_ctx {
     // second stream: the extrema scan of octave o overlaps the blurs of octaves > o, and the keypoint
     // sort overlaps the descriptor kernel (dependencies by events, no host involvement)
     cudaStream_t side_stream = nullptr;
+    cudaStream_t blur_side_stream = nullptr;  // non-seeding layers of each octave (build_octaves)
+    cudaStream_t blur_stream = nullptr;       // launch override used by build_octaves, else `stream`
+    cudaEvent_t ev_seed = nullptr, ev_blur_side = nullptr;
     cudaEvent_t ev_oct[b200::kMaxOctaves] = {}, ev_side = nullptr, ev_main = nullptr;
     bool oct_events_valid = false;
     float last_ms = 0.f;

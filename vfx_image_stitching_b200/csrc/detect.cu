@@ -471,25 +471,50 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
         const int nx = xhi - xlo + 1, ny = yhi - ylo + 1;
         const int total = (nx > 0 && ny > 0) ? nx * ny : 0;
         int yy = lane / max(nx, 1), xx = lane - yy * max(nx, 1);
-        // two pixels per lane and iteration (straight-line code: the two gather / sqrt / atan2 / exp
-        // chains overlap); the histogram updates stay in pixel order
+        // Two pixels per lane and iteration (straight-line code: the two sqrt / atan2 / exp chains
+        // overlap), and the gather of iteration i+1 is issued before the arithmetic of iteration i so
+        // that its L2 latency is covered; the histogram updates stay in pixel order.
+        int ny_[2], nx_[2];      // pixel coordinates of the iteration in flight
+        bool nlive[2];
+        float ng[2][4];
+        auto issue = [&](int idx) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                nlive[u] = idx + 32 * u < total;
+                ny_[u] = nlive[u] ? ylo + yy : ylo;
+                nx_[u] = nlive[u] ? xlo + xx : xlo;
+                xx += 32;
+                while (xx >= nx) { xx -= nx; ++yy; }
+                const float *p = gimg + (size_t)ny_[u] * pitch + nx_[u];
+                ng[u][0] = __ldg(p + 1);
+                ng[u][1] = __ldg(p - 1);
+                ng[u][2] = __ldg(p - pitch);
+                ng[u][3] = __ldg(p + pitch);
+            }
+        };
+        if (total > 0) issue(lane);
         for (int idx = lane; idx < total; idx += 64) {
+            int cyv[2], cxv[2];
+            bool live[2];
+            float g[2][4];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                cyv[u] = ny_[u]; cxv[u] = nx_[u]; live[u] = nlive[u];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) g[u][k] = ng[u][k];
+            }
+            if (idx + 64 < total) issue(idx + 64);
             int bin[2];
             float val[2];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                const bool live = idx + 32 * u < total;
-                const int y = live ? ylo + yy : ylo, x = live ? xlo + xx : xlo;
-                const int dy = y - cy, dx = x - cx;
-                xx += 32;
-                while (xx >= nx) { xx -= nx; ++yy; }
-                const float *p = gimg + (size_t)y * pitch + x;
-                const float gx = p[1] - p[-1];
-                const float gy = p[-pitch] - p[pitch];
+                const int dy = cyv[u] - cy, dx = cxv[u] - cx;
+                const float gx = g[u][0] - g[u][1];
+                const float gy = g[u][2] - g[u][3];
                 const float mag = sqrtf(gx * gx + gy * gy);
                 const float ang = mod360f(atan2f(gy, gx) * B200_RAD2DEGF);
                 const float wgt = expf(weight_fac * (float)(dx * dx + dy * dy));
-                bin[u] = live ? (int)rintf(ang * (float)nb / 360.f) % nb : -1;
+                bin[u] = live[u] ? (int)rintf(ang * (float)nb / 360.f) % nb : -1;
                 val[u] = wgt * mag;
             }
 #pragma unroll
@@ -822,7 +847,7 @@ int run_detect(b200sift_ctx *c, const b200sift_params &p, int /*want_scan_order*
             refine_kernel<<<blocks, 128, 0, c->stream>>>(v, dp, c->d_cand, c->cand_cap, c->d_loc, c->loc_cap,
                                                          c->d_counters);
             c->launches++;
-            orient_kernel<<<c->sm_count * 4, kOriWarps * 32, 0, c->stream>>>(v, dp, c->d_loc, c->loc_cap, c->d_raw,
+            orient_kernel<<<c->sm_count * 5, kOriWarps * 32, 0, c->stream>>>(v, dp, c->d_loc, c->loc_cap, c->d_raw,
                                                                              c->raw_cap, c->d_counters);
             c->launches++;
         }

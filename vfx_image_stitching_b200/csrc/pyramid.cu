@@ -207,7 +207,7 @@ struct TailArgs {
     int radius[kMaxLayers];      // per layer (tap set index = layer)
     int n_img, n_oct, n_layers, o_tail, r_max;
 };
-constexpr int kTailThreads = 1024;
+constexpr int kTailThreads = 512;
 
 // One blur of the chain on the shared-memory resident octave: A (x-halo) -> B (y-halo) -> A, HBM.
 // R is a template parameter so that the tap loops unroll into straight LDS / FADD / FFMA runs.
@@ -359,7 +359,7 @@ static int launch_strip(b200sift_ctx *c, const float *src, float *dst, float *ds
     dim3 grid(strips, (h + seg - 1) / seg, n_img);
     BlurTaps<R> taps;
     memcpy(taps.t, g_taps[c->device & 15].taps[tapset], sizeof(taps.t));
-    blur_strip_kernel<R><<<grid, 256, smem, c->stream>>>(src, dst, dst2, h, w, pitch, img_stride, h2, w2, pitch2,
+    blur_strip_kernel<R><<<grid, 256, smem, c->blur_stream ? c->blur_stream : c->stream>>>(src, dst, dst2, h, w, pitch, img_stride, h2, w2, pitch2,
                                                          img_stride2, seg, taps);
     c->launches++;
     B200_CUDA(cudaGetLastError());
@@ -395,7 +395,7 @@ static int launch_blur_set(b200sift_ctx *c, const float *src, float *dst, int n_
         attr_smem = smem;
     }
     dim3 grid((w + 31) / 32, (h + 31) / 32, n_img);
-    blur_tile_kernel<<<grid, 256, smem, c->stream>>>(src, dst, dst2, h, w, pitch, img_stride, h2, w2, pitch2,
+    blur_tile_kernel<<<grid, 256, smem, c->blur_stream ? c->blur_stream : c->stream>>>(src, dst, dst2, h, w, pitch, img_stride, h2, w2, pitch2,
                                                      img_stride2, R, tapset);
     c->launches++;
     B200_CUDA(cudaGetLastError());
@@ -480,22 +480,39 @@ int build_octaves(b200sift_ctx *c, const double *sigmas)
             }
         }
     }
+    // Critical path of the pyramid: layers 1..n-3 of octave o, whose last one seeds octave o+1
+    // (sift_impl.py:95-96).  The remaining layers of octave o feed nothing downstream but the
+    // extrema scan, so they go to a second stream and overlap the (small, latency-bound) blurs of
+    // the following octaves.
+    const int l_seed = p.n_layers - 3;
+    const bool split = l_seed >= 1 && l_seed < p.n_layers - 1 && p.n_oct > 1;
+    bool side_used = false;
     for (int o = 0; o < o_tail; ++o) {
         for (int l = 1; l < p.n_layers; ++l) {
             float *dst2 = nullptr;
             int h2 = 0, w2 = 0, pitch2 = 0;
             size_t is2 = 0;
-            if (l == p.n_layers - 3 && o + 1 < p.n_oct) {
+            if (l == l_seed && o + 1 < p.n_oct) {
                 dst2 = p.layer(o + 1, 0);
                 h2 = p.h[o + 1];
                 w2 = p.w[o + 1];
                 pitch2 = p.pitch[o + 1];
                 is2 = p.img_stride(o + 1);
             }
-            B200_CHECK(launch_blur_set(c, p.layer(o, l - 1), p.layer(o, l), p.n_img, p.h[o], p.w[o], p.pitch[o],
-                                       p.img_stride(o), R[l], l, dst2, h2, w2, pitch2, is2));
+            const bool on_side = split && l > l_seed;
+            if (on_side && l == l_seed + 1) {
+                B200_CUDA(cudaEventRecord(c->ev_seed, c->stream));
+                B200_CUDA(cudaStreamWaitEvent(c->blur_side_stream, c->ev_seed, 0));
+                side_used = true;
+            }
+            c->blur_stream = on_side ? c->blur_side_stream : nullptr;
+            const int rc = launch_blur_set(c, p.layer(o, l - 1), p.layer(o, l), p.n_img, p.h[o], p.w[o], p.pitch[o],
+                                           p.img_stride(o), R[l], l, dst2, h2, w2, pitch2, is2);
+            c->blur_stream = nullptr;
+            B200_CHECK(rc);
         }
-        B200_CUDA(cudaEventRecord(c->ev_oct[o], c->stream));  // all layers of octave o are complete
+        // all layers of octave o are complete
+        B200_CUDA(cudaEventRecord(c->ev_oct[o], split ? c->blur_side_stream : c->stream));
     }
     if (o_tail < p.n_oct) {
         TailArgs a;
@@ -510,6 +527,10 @@ int build_octaves(b200sift_ctx *c, const double *sigmas)
         B200_CUDA(cudaGetLastError());
         c->launches++;
         for (int o = o_tail; o < p.n_oct; ++o) B200_CUDA(cudaEventRecord(c->ev_oct[o], c->stream));
+    }
+    if (side_used) {  // later work on the main stream sees the whole pyramid
+        B200_CUDA(cudaEventRecord(c->ev_blur_side, c->blur_side_stream));
+        B200_CUDA(cudaStreamWaitEvent(c->stream, c->ev_blur_side, 0));
     }
     c->oct_events_valid = true;
     return 0;

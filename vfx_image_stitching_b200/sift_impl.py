@@ -129,7 +129,8 @@ def detect_and_describe_batch(images, sigma=1.6, num_intervals=3, assumed_blur=0
 
 def download_results(counts, ctx=None, out=None):
     """(keypoints, uint8 descriptors) of every image of the last detect, copied to the host in two
-    transfers.  `out` = optional (kps, desc) host arrays to fill (e.g. views of pinned memory)."""
+    transfers.  `counts` must be the counts of ALL images of that detect (the C side refuses a
+    short buffer).  `out` = optional (kps, desc) host arrays to fill (e.g. views of pinned memory)."""
     ctx = ctx or default_context()
     counts = np.asarray(counts, np.int64)
     total = int(counts.sum())
@@ -139,7 +140,7 @@ def download_results(counts, ctx=None, out=None):
     else:
         kps, desc = out[0][:total], out[1][:total]
     if total:
-        check(ctx.lib.b200sift_get_all_keypoints(ctx.handle, ptr(kps), ptr(desc)))
+        check(ctx.lib.b200sift_get_all_keypoints(ctx.handle, ptr(kps), ptr(desc), total))
     off = np.concatenate([[0], np.cumsum(counts)])
     return [(kps[off[i]:off[i + 1]], desc[off[i]:off[i + 1]]) for i in range(len(counts))]
 
