@@ -185,11 +185,26 @@ extrema_rows_kernel(PyrView v, int o, int border, float thresh, int n_cg, int n_
         for (int r = 0; r < 3; ++r) { hmx[l][r] = 0.f; hmn[l][r] = 0.f; }
 #pragma unroll
     for (int l = 0; l < NI; ++l) { dprev[l] = 0.f; dcur[l] = 0.f; }
+    // one pointer per Gaussian layer, stepped by `pitch` per row (no 64-bit address arithmetic in
+    // the loop), and the loads of row y+1 are issued before row y is evaluated
+    const float *pl[ND + 1];
+    float gn[ND + 1];
+#pragma unroll
+    for (int l = 0; l <= ND; ++l) {
+        pl[l] = g0 + (size_t)l * lstride + (size_t)(ybeg - 1) * pitch + xc;
+        gn[l] = __ldg(pl[l]);
+    }
     for (int y = ybeg - 1; y <= yend; ++y) {
-        const float *p = g0 + (size_t)y * pitch + xc;
         float g[ND + 1];
 #pragma unroll
-        for (int l = 0; l <= ND; ++l) g[l] = p[l * lstride];
+        for (int l = 0; l <= ND; ++l) g[l] = gn[l];
+        if (y < yend) {
+#pragma unroll
+            for (int l = 0; l <= ND; ++l) {
+                pl[l] += pitch;
+                gn[l] = __ldg(pl[l]);
+            }
+        }
 #pragma unroll
         for (int l = 0; l < ND; ++l) {
             const float d = __fsub_rn(g[l + 1], g[l]);

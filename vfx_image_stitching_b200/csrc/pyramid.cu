@@ -94,44 +94,72 @@ __device__ __forceinline__ float load_grey(const uint8_t *img, size_t row_stride
     return (float)((p[0] * 3735 + p[1] * 19235 + p[2] * 9798 + 16384) >> 15);
 }
 
+// One CTA converts a 16 x 64 source tile (+1 replicate-clamped halo) to grey in shared memory
+// once, then every thread produces 2 x 4 output pixels per step from 3 x 4 grey values: the
+// .25/.75 pattern of the exact 2x resize is fixed per output parity, only the image border
+// columns / rows differ (weight 1 on the edge pixel, as cv2's clamped coordinates give).
+constexpr int kUpH = 16, kUpW = 64;
+
 __global__ void __launch_bounds__(256) gray_upsample_kernel(const uint8_t *__restrict__ in, size_t img_stride_bytes,
                                                             const uint8_t *const *__restrict__ ptrs,
                                                             size_t row_stride, int h, int w, int channels, int dtype,
-                                                            float *__restrict__ out, int out_pitch)
+                                                            float *__restrict__ out, int out_pitch, int vec_ok)
 {
-    const int X = blockIdx.x * 32 + (threadIdx.x & 31);
-    const int Y = blockIdx.y * 8 + (threadIdx.x >> 5);
-    if (X >= 2 * w || Y >= 2 * h) return;
+    __shared__ __align__(16) float g[kUpH + 2][kUpW + 4];
+    const int tid = threadIdx.x;
+    const int sy0 = blockIdx.y * kUpH, sx0 = blockIdx.x * kUpW;
     // images either sit at a fixed stride behind `in` or are named one by one in `ptrs`
     const uint8_t *img = ptrs ? ptrs[blockIdx.z] : in + (size_t)blockIdx.z * img_stride_bytes;
-    int sx = (X & 1) ? (X >> 1) : (X >> 1) - 1;
-    float fx = (X & 1) ? 0.25f : 0.75f;
-    if (sx < 0) { sx = 0; fx = 0.f; }
-    int sx1 = sx + 1;
-    if (sx >= w - 1) { sx = w - 1; sx1 = w - 1; fx = 0.f; }
-    int sy = (Y & 1) ? (Y >> 1) : (Y >> 1) - 1;
-    float fy = (Y & 1) ? 0.25f : 0.75f;
-    if (sy < 0) { sy = 0; fy = 0.f; }
-    int sy1 = sy + 1;
-    if (sy >= h - 1) { sy = h - 1; sy1 = h - 1; fy = 0.f; }
-    float a = load_grey(img, row_stride, sy, sx, channels, dtype);
-    float b = load_grey(img, row_stride, sy, sx1, channels, dtype);
-    float c = load_grey(img, row_stride, sy1, sx, channels, dtype);
-    float d = load_grey(img, row_stride, sy1, sx1, channels, dtype);
-    float r0 = __fadd_rn(__fmul_rn(a, 1.f - fx), __fmul_rn(b, fx));
-    float r1 = __fadd_rn(__fmul_rn(c, 1.f - fx), __fmul_rn(d, fx));
-    float v = __fadd_rn(__fmul_rn(r0, 1.f - fy), __fmul_rn(r1, fy));
-    out[(size_t)blockIdx.z * (size_t)(2 * h) * out_pitch + (size_t)Y * out_pitch + X] = v;
+    for (int i = tid; i < (kUpH + 2) * (kUpW + 3); i += 256) {
+        const int r = i / (kUpW + 3), cc = i - r * (kUpW + 3);
+        const int y = min(max(sy0 - 1 + r, 0), h - 1), x = min(max(sx0 - 1 + cc, 0), w - 1);
+        g[r][cc] = load_grey(img, row_stride, y, x, channels, dtype);
+    }
+    __syncthreads();
+    float *oimg = out + (size_t)blockIdx.z * (size_t)(2 * h) * out_pitch;
+    for (int u = tid; u < kUpH * (kUpW / 2); u += 256) {
+        const int i = u / (kUpW / 2), k = u - i * (kUpW / 2);
+        const int si = sy0 + i, sj = sx0 + 2 * k;  // source row / first of the two source columns
+        if (si >= h || sj >= w) continue;
+        // horizontal pass on source rows si-1, si, si+1 (tile rows i, i+1, i+2)
+        float H[3][4];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float2 q0 = *reinterpret_cast<const float2 *>(&g[i + r][2 * k]);      // columns sj-1, sj
+            const float2 q1 = *reinterpret_cast<const float2 *>(&g[i + r][2 * k + 2]);  // columns sj+1, sj+2
+            const float a = q0.x, b = q0.y, c = q1.x, d = q1.y;
+            H[r][0] = sj == 0 ? b : __fadd_rn(__fmul_rn(a, 0.25f), __fmul_rn(b, 0.75f));
+            H[r][1] = sj >= w - 1 ? b : __fadd_rn(__fmul_rn(b, 0.75f), __fmul_rn(c, 0.25f));
+            H[r][2] = __fadd_rn(__fmul_rn(b, 0.25f), __fmul_rn(c, 0.75f));
+            H[r][3] = sj + 1 >= w - 1 ? c : __fadd_rn(__fmul_rn(c, 0.75f), __fmul_rn(d, 0.25f));
+        }
+        float o0[4], o1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            o0[j] = si == 0 ? H[1][j] : __fadd_rn(__fmul_rn(H[0][j], 0.25f), __fmul_rn(H[1][j], 0.75f));
+            o1[j] = si >= h - 1 ? H[1][j] : __fadd_rn(__fmul_rn(H[1][j], 0.75f), __fmul_rn(H[2][j], 0.25f));
+        }
+        float *p0 = oimg + (size_t)(2 * si) * out_pitch + 2 * sj, *p1 = p0 + out_pitch;
+        if (vec_ok && sj + 1 < w) {
+            *reinterpret_cast<float4 *>(p0) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+            *reinterpret_cast<float4 *>(p1) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+        } else {
+            const int nv = sj + 1 < w ? 4 : 2;
+            for (int j = 0; j < nv; ++j) { p0[j] = o0[j]; p1[j] = o1[j]; }
+        }
+    }
 }
 
 int launch_gray_upsample(b200sift_ctx *c, const void *d_in, size_t img_stride_bytes, const void *const *d_ptrs,
                          size_t row_stride, int n_img, int h, int w, int channels, int dtype, float *d_out,
                          int out_pitch)
 {
-    dim3 grid((2 * w + 31) / 32, (2 * h + 7) / 8, n_img);
+    dim3 grid((w + kUpW - 1) / kUpW, (h + kUpH - 1) / kUpH, n_img);
+    const int vec_ok = (out_pitch % 4 == 0) && (((size_t)(2 * h) * out_pitch) % 4 == 0) &&
+                       (reinterpret_cast<uintptr_t>(d_out) % 16 == 0);
     gray_upsample_kernel<<<grid, 256, 0, c->stream>>>((const uint8_t *)d_in, img_stride_bytes,
                                                       (const uint8_t *const *)d_ptrs, row_stride, h, w, channels,
-                                                      dtype, d_out, out_pitch);
+                                                      dtype, d_out, out_pitch, vec_ok);
     c->launches++;
     B200_CUDA(cudaGetLastError());
     return 0;
