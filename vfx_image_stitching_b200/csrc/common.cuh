@@ -116,6 +116,7 @@ struct b200sift_ctx {
     // sort overlaps the descriptor kernel (dependencies by events, no host involvement)
     cudaStream_t side_stream = nullptr;
     cudaStream_t blur_side_stream = nullptr;  // non-seeding layers of each octave (build_octaves)
+    int pyr_o_tail = 0;                       // first octave produced by the pyramid tail kernel (0 = none)
     cudaStream_t blur_stream = nullptr;       // launch override used by build_octaves, else `stream`
     cudaEvent_t ev_seed = nullptr, ev_blur_side = nullptr;
     cudaEvent_t ev_oct[b200::kMaxOctaves] = {}, ev_side = nullptr, ev_main = nullptr;

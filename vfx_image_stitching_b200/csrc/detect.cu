@@ -158,17 +158,27 @@ extrema_kernel(PyrView v, int o, int border, int num_intervals, float thresh, Ca
 // likewise with min for negative values.  Each Gaussian value is read once
 // from HBM (24 B per pixel for 6 layers, + halo rows / lanes from L2).
 // ---------------------------------------------------------------------------
-constexpr int kExSegRows = 32;
+// One launch scans a GROUP of consecutive octaves (the small octaves of the pyramid tail are
+// ready at the same time; one launch per octave there is pure latency on the critical path).
+struct ExGroup {
+    int o_first, n_oct;
+    int blk_off[kMaxOctaves + 1];  // first block of each octave of the group
+    int n_cg[kMaxOctaves], n_rs[kMaxOctaves], seg_rows[kMaxOctaves];
+};
 
 template <int NI>
 __global__ void __launch_bounds__(256)
-extrema_rows_kernel(PyrView v, int o, int border, float thresh, int n_cg, int n_rs, Candidate *__restrict__ cand,
-                    int cand_cap, int32_t *__restrict__ counters)
+extrema_rows_kernel(PyrView v, const __grid_constant__ ExGroup grp, int border, float thresh,
+                    Candidate *__restrict__ cand, int cand_cap, int32_t *__restrict__ counters)
 {
     constexpr int ND = NI + 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int img = blockIdx.y;
-    const int item = blockIdx.x * 8 + warp;
+    int gi = 0;
+    while (gi + 1 < grp.n_oct && (int)blockIdx.x >= grp.blk_off[gi + 1]) ++gi;
+    const int o = grp.o_first + gi;
+    const int n_cg = grp.n_cg[gi], n_rs = grp.n_rs[gi], seg_rows = grp.seg_rows[gi];
+    const int item = ((int)blockIdx.x - grp.blk_off[gi]) * 8 + warp;
     if (item >= n_cg * n_rs) return;  // whole warp
     const int cg = item % n_cg, rs = item / n_cg;
     const int h = v.h[o], w = v.w[o], pitch = v.pitch[o];
@@ -177,7 +187,7 @@ extrema_rows_kernel(PyrView v, int o, int border, float thresh, int n_cg, int n_
     const int x = border + 30 * cg - 1 + lane;
     const int xc = min(x, w - 1);
     const bool out_lane = (lane >= 1) && (lane <= 30) && (x < w - border);
-    const int ybeg = border + rs * kExSegRows, yend = min(ybeg + kExSegRows, h - border);
+    const int ybeg = border + rs * seg_rows, yend = min(ybeg + seg_rows, h - border);
     float hmx[ND][3], hmn[ND][3], dprev[NI], dcur[NI];
 #pragma unroll
     for (int l = 0; l < ND; ++l)
@@ -835,21 +845,39 @@ int run_detect(b200sift_ctx *c, const b200sift_params &p, int /*want_scan_order*
         cudaStream_t es = overlap ? c->side_stream : c->stream;
         B200_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(int32_t) * n_cnt, es));
         const size_t ex_smem = (size_t)(py.n_layers - 1) * (kExTW + 2) * (kExTH + 2) * sizeof(float);
+        // octaves at or past `o_merge` (the ones the pyramid tail kernel produced together) share one launch
+        const int o_merge = (overlap && p.num_intervals == 3 && c->pyr_o_tail > 0) ? c->pyr_o_tail : py.n_oct;
         for (int o = 0; o < py.n_oct; ++o) {
             const int sh = py.h[o] - 2 * p.image_border_width, sw = py.w[o] - 2 * p.image_border_width;
             if (sh <= 0 || sw <= 0) continue;
             if (overlap) B200_CUDA(cudaStreamWaitEvent(es, c->ev_oct[o], 0));
-            if (p.num_intervals == 3 && sw >= 24) {
-                const int n_cg = (sw + 29) / 30, n_rs = (sh + kExSegRows - 1) / kExSegRows;
-                dim3 grid((n_cg * n_rs + 7) / 8, py.n_img);
-                extrema_rows_kernel<3><<<grid, 256, 0, es>>>(v, o, p.image_border_width, dp.dog_thresh, n_cg, n_rs,
-                                                            c->d_cand, c->cand_cap, c->d_counters);
+            if (p.num_intervals == 3 && (sw >= 24 || o >= o_merge)) {
+                ExGroup g;
+                g.o_first = o;
+                g.n_oct = 0;
+                g.blk_off[0] = 0;
+                const int o_end = o >= o_merge ? py.n_oct : o + 1;
+                int oo = o;
+                for (; oo < o_end; ++oo) {
+                    const int sh2 = py.h[oo] - 2 * p.image_border_width, sw2 = py.w[oo] - 2 * p.image_border_width;
+                    if (sh2 <= 0 || sw2 <= 0) break;  // every later octave is smaller still
+                    const int j = g.n_oct++;
+                    g.seg_rows[j] = py.h[oo] > 256 ? 32 : 8;
+                    g.n_cg[j] = (sw2 + 29) / 30;
+                    g.n_rs[j] = (sh2 + g.seg_rows[j] - 1) / g.seg_rows[j];
+                    g.blk_off[j + 1] = g.blk_off[j] + (g.n_cg[j] * g.n_rs[j] + 7) / 8;
+                }
+                dim3 grid(g.blk_off[g.n_oct], py.n_img);
+                extrema_rows_kernel<3><<<grid, 256, 0, es>>>(v, g, p.image_border_width, dp.dog_thresh, c->d_cand,
+                                                            c->cand_cap, c->d_counters);
+                c->launches++;
+                if (o >= o_merge) break;  // the group covered every remaining octave
             } else {
                 dim3 grid((sw + kExTW - 1) / kExTW, (sh + kExTH - 1) / kExTH, py.n_img);
                 extrema_kernel<<<grid, 256, ex_smem, es>>>(v, o, p.image_border_width, p.num_intervals, dp.dog_thresh,
                                                            c->d_cand, c->cand_cap, c->d_counters);
+                c->launches++;
             }
-            c->launches++;
         }
         if (overlap) {
             B200_CUDA(cudaEventRecord(c->ev_side, es));

@@ -241,12 +241,20 @@ constexpr int kTailThreads = 512;
 // R is a template parameter so that the tap loops unroll into straight LDS / FADD / FFMA runs.
 // Lanes past the right / bottom edge compute on whatever lies there (inside the allocation, see
 // tail_smem_bytes) and only the stores are predicated.
+// Fixed shared-memory pitches (tail octaves are <= 128 px wide, radii <= 16): every tap of both
+// passes is an LDS with an immediate offset, and the flattened (row, unit) loops use shifts
+// (lw = log2 of the width rounded up to a power of two) instead of divisions.
+constexpr int kTailRm = 16;                 // halo reserved on each side of A and B
+constexpr int kTailPA = 128 + 2 * kTailRm;  // A[h][kTailPA], interior starts at column kTailRm
+constexpr int kTailPB = 128;                // B[h + 2*kTailRm + 3][kTailPB], interior starts at row kTailRm
+
 template <int R>
-__device__ __forceinline__ void tail_layer(float *A, float *B, const float *__restrict__ taps, int h, int w, int Rm,
+__device__ __forceinline__ void tail_layer(float *A, float *B, const float *__restrict__ taps, int h, int w, int lw,
                                            float *__restrict__ dst, int pitch, float *__restrict__ dst2, int h2,
                                            int w2, int pitch2)
 {
-    const int tid = threadIdx.x, pa = w + 2 * Rm;
+    constexpr int Rm = kTailRm, PA = kTailPA, PB = kTailPB;
+    const int tid = threadIdx.x;
     float t[R + 1];
 #pragma unroll
     for (int k = 0; k <= R; ++k) t[k] = taps[k];
@@ -254,42 +262,46 @@ __device__ __forceinline__ void tail_layer(float *A, float *B, const float *__re
     for (int i = tid; i < h * 2 * R; i += kTailThreads) {
         const int y = i / (2 * R), k = i - y * (2 * R);
         const int x = k < R ? k - R : w + (k - R);  // -R..-1, w..w+R-1
-        A[y * pa + Rm + x] = A[y * pa + Rm + reflect101(x, w)];
+        A[y * PA + Rm + x] = A[y * PA + Rm + reflect101(x, w)];
     }
     __syncthreads();
     // row pass: 4 adjacent x per thread, A -> B interior rows
-    const int xb = (w + 3) >> 2;
-    for (int i = tid; i < h * xb; i += kTailThreads) {
-        const int y = i / xb, x0 = (i - y * xb) * 4;
-        const float *p = A + y * pa + Rm + x0 - R;
+    const int lxb = lw >= 2 ? lw - 2 : 0;  // log2 of the (padded) number of 4-column units per row
+    for (int i = tid; i < (h << lxb); i += kTailThreads) {
+        const int y = i >> lxb, x0 = (i & ((1 << lxb) - 1)) * 4;
+        if (x0 >= w) continue;
+        const float *p = A + y * PA + Rm + x0 - R;
         float v[4 + 2 * R];
 #pragma unroll
         for (int q = 0; q < 4 + 2 * R; ++q) v[q] = p[q];
-        float *o = B + (y + Rm) * w + x0;
+        float acc[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float acc = t[0] * v[j + R];
+            acc[j] = t[0] * v[j + R];
 #pragma unroll
-            for (int k = 1; k <= R; ++k) acc = fmaf(t[k], v[j + R + k] + v[j + R - k], acc);
-            if (x0 + j < w) o[j] = acc;
+            for (int k = 1; k <= R; ++k) acc[j] = fmaf(t[k], v[j + R + k] + v[j + R - k], acc[j]);
         }
+        // columns past w land in B's padding (PB >= w rounded up to 4) and are never read back
+        *reinterpret_cast<float4 *>(B + (y + Rm) * PB + x0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     }
     __syncthreads();
     // reflected y-halo of B
-    for (int i = tid; i < 2 * R * w; i += kTailThreads) {
-        const int k = i / w, x = i - k * w;
+    for (int i = tid; i < ((2 * R) << lw); i += kTailThreads) {
+        const int k = i >> lw, x = i & ((1 << lw) - 1);
+        if (x >= w) continue;
         const int y = k < R ? k - R : h + (k - R);
-        B[(y + Rm) * w + x] = B[(reflect101(y, h) + Rm) * w + x];
+        B[(y + Rm) * PB + x] = B[(reflect101(y, h) + Rm) * PB + x];
     }
     __syncthreads();
     // column pass: 4 adjacent y per thread, B -> HBM layer, A interior, decimated seed
     const int yb = (h + 3) >> 2;
-    for (int i = tid; i < yb * w; i += kTailThreads) {
-        const int yblk = i / w, x = i - yblk * w, y0 = yblk * 4;
-        const float *p = B + (y0 + Rm - R) * w + x;
+    for (int i = tid; i < (yb << lw); i += kTailThreads) {
+        const int yblk = i >> lw, x = i & ((1 << lw) - 1), y0 = yblk * 4;
+        if (x >= w) continue;
+        const float *p = B + (y0 + Rm - R) * PB + x;
         float v[4 + 2 * R];
 #pragma unroll
-        for (int q = 0; q < 4 + 2 * R; ++q) v[q] = p[q * w];
+        for (int q = 0; q < 4 + 2 * R; ++q) v[q] = p[q * PB];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             float acc = t[0] * v[j + R];
@@ -297,7 +309,7 @@ __device__ __forceinline__ void tail_layer(float *A, float *B, const float *__re
             for (int k = 1; k <= R; ++k) acc = fmaf(t[k], v[j + R + k] + v[j + R - k], acc);
             const int y = y0 + j;
             if (y < h) {
-                A[y * pa + Rm + x] = acc;
+                A[y * PA + Rm + x] = acc;
                 dst[(size_t)y * pitch + x] = acc;
                 if (dst2 && !((y | x) & 1) && (y >> 1) < h2 && (x >> 1) < w2)
                     dst2[(size_t)(y >> 1) * pitch2 + (x >> 1)] = acc;
@@ -307,30 +319,31 @@ __device__ __forceinline__ void tail_layer(float *A, float *B, const float *__re
     __syncthreads();
 }
 
-// floats of shared memory for a first tail octave of h0 x w0: A, B and 3 rows of slack for the
-// unpredicated reads of tail_layer
-static size_t tail_smem_bytes(int h0, int w0, int r_max)
+// bytes of shared memory for a first tail octave of h0 rows: A, B (with 3 rows of slack for the
+// unpredicated reads of the column pass)
+static size_t tail_smem_bytes(int h0)
 {
-    return ((size_t)h0 * (w0 + 2 * r_max) + (size_t)(h0 + 2 * r_max + 3) * w0 + 8) * sizeof(float);
+    return ((size_t)h0 * kTailPA + (size_t)(h0 + 2 * kTailRm + 3) * kTailPB) * sizeof(float);
 }
 
 __global__ void __launch_bounds__(kTailThreads) pyramid_tail_kernel(const __grid_constant__ TailArgs a)
 {
     extern __shared__ __align__(16) float smem[];
-    const int img = blockIdx.x, tid = threadIdx.x, Rm = a.r_max;
-    const int h0 = a.h[a.o_tail], w0 = a.w[a.o_tail];
-    float *A = smem;                        // [h][w + 2Rm], sized for the first tail octave
-    float *B = smem + h0 * (w0 + 2 * Rm);   // [h + 2Rm (+3)][w]
+    const int img = blockIdx.x, tid = threadIdx.x;
+    const int h0 = a.h[a.o_tail];
+    float *A = smem;                // [h0][kTailPA]
+    float *B = smem + h0 * kTailPA; // [h0 + 2*kTailRm + 3][kTailPB]
     for (int o = a.o_tail; o < a.n_oct; ++o) {
         const int h = a.h[o], w = a.w[o], pitch = a.pitch[o];
         const size_t istride = (size_t)h * pitch;
-        const int pa = w + 2 * Rm;
+        int lw = 0;
+        while ((1 << lw) < w) ++lw;
         // layer 0 of this octave -> A interior (written by the previous kernel, or by this CTA below)
         {
             const float *src = a.base + a.oct_off[o] + (size_t)img * istride;
-            for (int i = tid; i < h * w; i += kTailThreads) {
-                const int y = i / w, x = i - y * w;
-                A[y * pa + Rm + x] = __ldcg(&src[(size_t)y * pitch + x]);
+            for (int i = tid; i < (h << lw); i += kTailThreads) {
+                const int y = i >> lw, x = i & ((1 << lw) - 1);
+                if (x < w) A[y * kTailPA + kTailRm + x] = __ldcg(&src[(size_t)y * pitch + x]);
             }
         }
         __syncthreads();
@@ -345,7 +358,7 @@ __global__ void __launch_bounds__(kTailThreads) pyramid_tail_kernel(const __grid
                 dst2 = a.base + a.oct_off[o + 1] + (size_t)img * ((size_t)h2 * pitch2);
             }
             switch (R) {
-#define B200_TAIL_CASE(RR) case RR: tail_layer<RR>(A, B, taps, h, w, Rm, dst, pitch, dst2, h2, w2, pitch2); break;
+#define B200_TAIL_CASE(RR) case RR: tail_layer<RR>(A, B, taps, h, w, lw, dst, pitch, dst2, h2, w2, pitch2); break;
                 B200_TAIL_CASE(1) B200_TAIL_CASE(2) B200_TAIL_CASE(3) B200_TAIL_CASE(4) B200_TAIL_CASE(5)
                 B200_TAIL_CASE(6) B200_TAIL_CASE(7) B200_TAIL_CASE(8) B200_TAIL_CASE(9) B200_TAIL_CASE(10)
                 B200_TAIL_CASE(11) B200_TAIL_CASE(12) B200_TAIL_CASE(13) B200_TAIL_CASE(14) B200_TAIL_CASE(15)
@@ -496,8 +509,9 @@ int build_octaves(b200sift_ctx *c, const double *sigmas)
     if (o_tail < p.n_oct) {
         for (int l = 1; l < p.n_layers; ++l) max_r = R[l] > max_r ? R[l] : max_r;
         const int h0 = p.h[o_tail], w0 = p.w[o_tail];
-        tail_smem = tail_smem_bytes(h0, w0, max_r);
-        if (tail_smem > 200 * 1024 || max_r > 16) {
+        (void)w0;
+        tail_smem = tail_smem_bytes(h0);
+        if (tail_smem > 200 * 1024 || max_r > kTailRm) {
             o_tail = p.n_oct;
         } else {
             static size_t attr_smem = 48 * 1024;
@@ -560,6 +574,7 @@ int build_octaves(b200sift_ctx *c, const double *sigmas)
         B200_CUDA(cudaEventRecord(c->ev_blur_side, c->blur_side_stream));
         B200_CUDA(cudaStreamWaitEvent(c->stream, c->ev_blur_side, 0));
     }
+    c->pyr_o_tail = o_tail < p.n_oct ? o_tail : 0;
     c->oct_events_valid = true;
     return 0;
 }
