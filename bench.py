@@ -203,15 +203,28 @@ def main():
             return iss.panorama_shifts(resident, ctx=ctx)          # [(dx, dy)] * 17, like the reference loop
         return panorama.sharded_panorama_shifts(resident, backend, dist=dist, device=dev)
 
+    # e2e outputs land in pinned host memory as well (allocated once, grown on demand)
+    out_pin = {}
+
+    def pinned_out(total):
+        if out_pin.get('cap', 0) < total:
+            cap = max(2 * total, 1 << 16)
+            kp_bytes = torch.empty(cap * sift_impl.KP_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+            desc = torch.empty((cap, 128), dtype=torch.uint8).pin_memory()
+            out_pin.update(cap=cap, keep=(kp_bytes, desc),
+                           kps=kp_bytes.numpy().view(sift_impl.KP_DTYPE), desc=desc.numpy())
+        return out_pin['kps'], out_pin['desc']
+
     def step_e2e():
         """host images in, host keypoints + descriptors + shifts out."""
         if world == 1:
             counts = sift_impl.detect_and_describe_batch(pinned_np, ctx=ctx, download=False)
             shifts = iss.match_pairs([(i, i + 1) for i in range(n - 1)], 3, 25000, ctx)[0]
-            res = sift_impl.download_results(counts, ctx)
+            res = sift_impl.download_results(counts, ctx, out=pinned_out(int(np.sum(counts))))
             return shifts, counts, res
         shifts, counts = panorama.sharded_panorama_shifts(pinned_np, backend, dist=dist, device=dev)
-        res = sift_impl.download_results(backend.counts, ctx)       # this rank's block, to the host
+        res = sift_impl.download_results(backend.counts, ctx,        # this rank's block, to the host
+                                         out=pinned_out(int(np.sum(backend.counts))))
         return shifts, counts, res
 
     def timed(fn, steps, warmup):

@@ -308,7 +308,7 @@ int b200sift_detect_describe(b200sift_ctx *c, const b200sift_params *params, int
     tr.mark(c, "extrema+refine+orient");
     fill_stats(c);
     const int n_raw = c->h_counters[CNT_RAW];
-    B200_CHECK(run_sort_async(c, n_raw, n_images, 0));          // side stream, overlaps the descriptors
+    B200_CHECK(run_sort_async(c, n_raw, n_images, 0, 1));         // side stream, overlaps the descriptors
     B200_CHECK(run_describe(c, P, c->d_raw, n_raw, 0, c->d_raw_desc));
     tr.mark(c, "describe (|| sort)");
     B200_CHECK(run_gather(c, n_raw, n_images, 1, 1, 1));

@@ -116,6 +116,8 @@ struct b200sift_ctx {
     // sort overlaps the descriptor kernel (dependencies by events, no host involvement)
     cudaStream_t side_stream = nullptr;
     cudaStream_t blur_side_stream = nullptr;  // non-seeding layers of each octave (build_octaves)
+    bool sort_fast = false;                   // last run_sort_async took the per-image shared-memory path
+    int sort_dedupe = 0;
     int pyr_o_tail = 0;                       // first octave produced by the pyramid tail kernel (0 = none)
     cudaStream_t blur_stream = nullptr;       // launch override used by build_octaves, else `stream`
     cudaEvent_t ev_seed = nullptr, ev_blur_side = nullptr;
@@ -200,7 +202,7 @@ int run_detect(b200sift_ctx *c, const b200sift_params &p, int want_scan_order);
 int run_describe(b200sift_ctx *c, const b200sift_params &p, const RawKeypoint *d_raw, int n, int converted,
                  uint8_t *d_out);
 int run_sort_gather(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int dedupe, int convert, int with_desc);
-int run_sort_async(b200sift_ctx *c, int n_raw, int n_img, int scan_order);   // on the side stream
+int run_sort_async(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int dedupe);   // on the side stream
 int run_gather(b200sift_ctx *c, int n_raw, int n_img, int dedupe, int convert, int with_desc);
 int ensure_sparse_for(b200sift_ctx *c, int n_img, int n_raw);
 int launch_ransac(b200sift_ctx *c, const float *d_matches, int n, double thr, double *move, int32_t *best);

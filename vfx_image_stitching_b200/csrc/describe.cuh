@@ -22,7 +22,8 @@
 
 constexpr int kDescWarps = 4;
 constexpr int kDescHistFloats = 128 * 32;
-constexpr int kDescQueue = 96;
+constexpr int kDescU = 2;                       // surviving pixels evaluated per lane and batch
+constexpr int kDescQueue = 32 * kDescU + 32;
 constexpr size_t kDescSmemPerWarp = kDescHistFloats * sizeof(float) + 2 * kDescQueue * sizeof(int);
 
 __global__ void __launch_bounds__(kDescWarps * 32, 3)
@@ -35,6 +36,7 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
     int *qx = reinterpret_cast<int *>(hist + kDescHistFloats);
     int *qy = qx + kDescQueue;
     const int warps_total = gridDim.x * kDescWarps;
+    constexpr int U = kDescU;
     const unsigned lt_mask = (1u << lane) - 1u;
     (void)warps_total;
     // keypoint windows differ 6x in size: warps take the next keypoint from a global counter
@@ -85,9 +87,9 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
         // window, so the address is always valid).  Issued one batch AHEAD of scatter2: the L2
         // latency of the gather (the shared-memory histograms leave almost no L1) is covered by the
         // arithmetic of the previous batch instead of stalling the warp.
-        auto gather4 = [&](const int (&xs)[2], const int (&ys)[2], float (&g)[2][4]) {
+        auto gather4 = [&](const int (&xs)[U], const int (&ys)[U], float (&g)[U][4]) {
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const float *p = img + (size_t)(pty + ys[u]) * pitch + (ptx + xs[u]);
                 g[u][0] = __ldg(p + 1);
                 g[u][1] = __ldg(p - 1);
@@ -95,13 +97,13 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
                 g[u][3] = __ldg(p + pitch);
             }
         };
-        auto scatter2 = [&](const int (&xs)[2], const int (&ys)[2], const bool (&live)[2], const float (&g)[2][4]) {
-            bool okc[2][4];
-            float *cell[2][4];
-            float mv[2][4], w0[2], w1[2];
-            int o0[2], o1[2];
+        auto scatter2 = [&](const int (&xs)[U], const int (&ys)[U], const bool (&live)[U], const float (&g)[U][4]) {
+            bool okc[U][4];
+            float *cell[U][4];
+            float mv[U][4], w0[U], w1[U];
+            int o0[U], o1[U];
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const double r_rot = xs[u] * sin_a + ys[u] * cos_a;
                 const double c_rot = xs[u] * cos_a - ys[u] * sin_a;
                 const double qr = r_rot * inv_hw, qc = c_rot * inv_hw;
@@ -139,7 +141,7 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
             // The eight bins of one pixel are distinct: all loads before the first store.  The
             // second pixel may hit the same bins, so it is applied after the first one's stores.
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < U; ++u) {
                 float h0[4], h1[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -163,10 +165,12 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
         const int total = (ok && nx > 0 && ny > 0) ? nx * ny : 0;
         int yy = lane / max(nx, 1), xx = lane - yy * max(nx, 1);
         int qn = 0;  // warp-uniform queue length
-        int px[2] = {0, 0}, py[2] = {0, 0};  // batch whose gather is in flight
-        float pg[2][4];
-        bool pending = false;                // warp-uniform
-        const bool all_live[2] = {true, true};
+        int px[U], py[U];  // batch whose gather is in flight
+        float pg[U][4];
+        bool all_live[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) { px[u] = 0; py[u] = 0; all_live[u] = true; }
+        bool pending = false;  // warp-uniform
         for (int idx0 = 0; idx0 < total; idx0 += 32) {
             const int ys = rlo + yy - pty, xs = clo + xx - ptx;
             xx += 32;
@@ -182,18 +186,20 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
             }
             qn += __popc(m);
             __syncwarp();
-            if (qn >= 64) {
-                const int sx[2] = {qx[lane], qx[lane + 32]}, sy[2] = {qy[lane], qy[lane + 32]};
-                const int tx = qx[lane + 64], ty = qy[lane + 64];
+            if (qn >= 32 * U) {
+                int sx[U], sy[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) { sx[u] = qx[lane + 32 * u]; sy[u] = qy[lane + 32 * u]; }
+                const int tx = qx[lane + 32 * U], ty = qy[lane + 32 * U];
                 __syncwarp();
-                qn -= 64;
+                qn -= 32 * U;
                 if (lane < qn) { qx[lane] = tx; qy[lane] = ty; }
-                float ng[2][4];
+                float ng[U][4];
                 gather4(sx, sy, ng);
                 if (pending) scatter2(px, py, all_live, pg);
                 pending = true;
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < U; ++u) {
                     px[u] = sx[u]; py[u] = sy[u];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) pg[u][k] = ng[u][k];
@@ -203,13 +209,18 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
         }
         {
             // drain: gather of the last (partial) batch goes out before the pending one is evaluated
-            int sx[2] = {0, 0}, sy[2] = {0, 0};
-            const bool live[2] = {lane < qn, lane + 32 < qn};
-            if (qn > 0) {  // dead lanes gather queue entry 0 (a valid address) and drop the result
-                sx[0] = qx[live[0] ? lane : 0]; sy[0] = qy[live[0] ? lane : 0];
-                sx[1] = qx[live[1] ? lane + 32 : 0]; sy[1] = qy[live[1] ? lane + 32 : 0];
+            int sx[U], sy[U];
+            bool live[U];
+            float ng[U][4];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                live[u] = lane + 32 * u < qn;
+                // dead lanes gather queue entry 0 (a valid address when qn > 0) and drop the result
+                sx[u] = qn > 0 ? qx[live[u] ? lane + 32 * u : 0] : 0;
+                sy[u] = qn > 0 ? qy[live[u] ? lane + 32 * u : 0] : 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ng[u][k] = 0.f;
             }
-            float ng[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
             if (qn > 0) gather4(sx, sy, ng);
             if (pending) scatter2(px, py, all_live, pg);
             if (qn > 0) scatter2(sx, sy, live, ng);

@@ -664,13 +664,16 @@ __global__ void __launch_bounds__(256)
 gather_kernel(const RawKeypoint *__restrict__ raw, const uint8_t *__restrict__ raw_desc,
               const uint32_t *__restrict__ idx, const uint32_t *__restrict__ keep, const uint32_t *__restrict__ pos,
               int n, int convert, b200sift_keypoint *__restrict__ kps, uint8_t *__restrict__ desc,
-              int32_t *__restrict__ counters)
+              int32_t *__restrict__ counters, const int *__restrict__ img_base)
 {
-    // 8 threads per keypoint: each moves 16 B of the descriptor
+    // 8 threads per keypoint: each moves 16 B of the descriptor.  pos[] is either the global output
+    // slot (scan over the whole list) or, with img_base, the slot inside the keypoint's image
+    // (written by sort_image_kernel; the per-image counters are then already final).
     const int t = blockIdx.x * 256 + threadIdx.x;
     const int i = t >> 3, part = t & 7;
     if (i >= n || !keep[i]) return;
-    const uint32_t src = idx[i], dst = pos[i];
+    const uint32_t src = idx[i];
+    const uint32_t dst = img_base ? (uint32_t)img_base[raw[src].img] + pos[i] : pos[i];
     if (raw_desc)
         reinterpret_cast<uint4 *>(desc + (size_t)dst * 128)[part] =
             reinterpret_cast<const uint4 *>(raw_desc + (size_t)src * 128)[part];
@@ -686,8 +689,10 @@ gather_kernel(const RawKeypoint *__restrict__ raw, const uint8_t *__restrict__ r
         k.angle = r.angle;
         k.response = r.response;
         kps[dst] = k;
-        atomicAdd(&counters[CNT_HDR + r.img * CNT_PER_IMG + 3], 1);
-        atomicAdd(&counters[CNT_OUT], 1);
+        if (!img_base) {
+            atomicAdd(&counters[CNT_HDR + r.img * CNT_PER_IMG + 3], 1);
+            atomicAdd(&counters[CNT_OUT], 1);
+        }
     }
 }
 
@@ -733,8 +738,11 @@ struct SortKeys {
 
 __global__ void __launch_bounds__(1024)
 sort_image_kernel(const RawKeypoint *__restrict__ raw, const int *__restrict__ seg_off,
-                  const uint32_t *__restrict__ idx_in, uint32_t *__restrict__ idx_out, int scan_order, int P_max)
+                  const uint32_t *__restrict__ idx_in, uint32_t *__restrict__ idx_out, int scan_order, int P_max,
+                  int dedupe, uint32_t *__restrict__ keep, uint32_t *__restrict__ pos_out,
+                  int *__restrict__ img_kept)
 {
+    __shared__ int wsum[32];
     extern __shared__ __align__(16) unsigned char ssm[];
     SortKeys K;
     K.order = reinterpret_cast<unsigned long long *>(ssm);
@@ -743,7 +751,10 @@ sort_image_kernel(const RawKeypoint *__restrict__ raw, const int *__restrict__ s
     uint32_t *rid = reinterpret_cast<uint32_t *>(K.resp + P_max);
     uint32_t *perm = rid + P_max;
     const int base = seg_off[blockIdx.x], n = seg_off[blockIdx.x + 1] - base;
-    if (n <= 0) return;
+    if (n <= 0) {
+        if (threadIdx.x == 0) img_kept[blockIdx.x] = 0;
+        return;
+    }
     int P = 2;
     while (P < n) P <<= 1;
     for (int s = threadIdx.x; s < P; s += 1024) {
@@ -774,6 +785,74 @@ sort_image_kernel(const RawKeypoint *__restrict__ raw, const int *__restrict__ s
         }
     }
     for (int s = threadIdx.x; s < n; s += 1024) idx_out[base + s] = rid[perm[s]];
+    // remove_duplicate_keypoints (:313-327) on the sorted list: keep flag and the slot inside this
+    // image's output (block-wide exclusive scan, 1024 entries per round).  idx_in aliases pos_out:
+    // this CTA's segment of it was consumed above.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int running = 0;
+    for (int s0 = 0; s0 < n; s0 += 1024) {
+        const int s = s0 + threadIdx.x;
+        int k = 0;
+        if (s < n) {
+            k = 1;
+            if (dedupe && s > 0) {
+                const uint32_t a = perm[s - 1], b = perm[s];
+                if (K.x[a] == K.x[b] && K.y[a] == K.y[b] && K.size[a] == K.size[b] && K.angle[a] == K.angle[b]) k = 0;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) wsum[warp] = __popc(m);
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int wv = 0; wv < 32; ++wv) {
+            const int c = wsum[wv];
+            if (wv < warp) woff += c;
+            tot += c;
+        }
+        if (s < n) {
+            keep[base + s] = (uint32_t)k;
+            pos_out[base + s] = (uint32_t)(running + woff + __popc(m & ((1u << lane) - 1u)));
+        }
+        running += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) img_kept[blockIdx.x] = running;
+}
+
+// Exclusive scan of the per-image kept counts -> first output slot of every image; also the final
+// per-image and total output counters (one CTA; n_img is small next to the keypoint lists).
+__global__ void __launch_bounds__(1024)
+image_offsets_kernel(const int *__restrict__ img_kept, int n_img, int *__restrict__ img_base,
+                     int32_t *__restrict__ counters)
+{
+    __shared__ int wsum[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int running = 0;
+    for (int i0 = 0; i0 < n_img; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        const int c = i < n_img ? img_kept[i] : 0;
+        int incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int woff = 0, tot = 0;
+        for (int wv = 0; wv < 32; ++wv) {
+            const int w = wsum[wv];
+            if (wv < warp) woff += w;
+            tot += w;
+        }
+        if (i < n_img) {
+            img_base[i] = running + woff + incl - c;
+            counters[CNT_HDR + i * CNT_PER_IMG + 3] = c;
+        }
+        running += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counters[CNT_OUT] = running;
 }
 
 static int ensure_sparse(b200sift_ctx *c, int cand_cap, int loc_cap, int raw_cap)
@@ -939,8 +1018,10 @@ int run_describe(b200sift_ctx *c, const b200sift_params &p, const RawKeypoint *d
 // optionally drop duplicates, convert and compact into c->d_kps / c->d_desc.
 // Ordering of the n raw keypoints (by image, then compare_keypoints or scan order) into
 // c->d_sort_idx, on the side stream; run_gather() joins it.
-int run_sort_async(b200sift_ctx *c, int n_raw, int n_img, int scan_order)
+int run_sort_async(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int dedupe)
 {
+    c->sort_fast = false;
+    c->sort_dedupe = dedupe;
     B200_CHECK(ensure_counters(c, n_img));
     c->img_off.assign(n_img + 1, 0);
     if (n_raw <= 0) return 0;
@@ -980,9 +1061,10 @@ int run_sort_async(b200sift_ctx *c, int n_raw, int n_img, int scan_order)
     }
     if (fast) {
         size_t cap = c->seg_cap;
-        B200_CHECK(ensure(&c->d_seg, &cap, (size_t)2 * (n_img + 1)));
+        B200_CHECK(ensure(&c->d_seg, &cap, (size_t)4 * (n_img + 1)));
         c->seg_cap = cap;
         int *d_off = c->d_seg, *d_cur = c->d_seg + (n_img + 1);
+        int *d_kept = c->d_seg + 2 * (n_img + 1), *d_base = c->d_seg + 3 * (n_img + 1);
         B200_CUDA(cudaMemcpyAsync(d_off, seg.data(), sizeof(int) * (n_img + 1), cudaMemcpyHostToDevice, ss));
         B200_CUDA(cudaMemsetAsync(d_cur, 0, sizeof(int) * (n_img + 1), ss));
         int P = 2;
@@ -995,8 +1077,11 @@ int run_sort_async(b200sift_ctx *c, int n_raw, int n_img, int scan_order)
         }
         // d_pos doubles as the bucketed (unsorted) index list; run_gather's scan rewrites it afterwards
         bucket_kernel<<<blocks, 256, 0, ss>>>(c->d_raw, n_raw, d_off, d_cur, c->d_pos);
-        sort_image_kernel<<<n_img, 1024, smem, ss>>>(c->d_raw, d_off, c->d_pos, c->d_sort_idx, scan_order, P);
-        c->launches += 2;
+        sort_image_kernel<<<n_img, 1024, smem, ss>>>(c->d_raw, d_off, c->d_pos, c->d_sort_idx, scan_order, P, dedupe,
+                                                     c->d_keep, c->d_pos, d_kept);
+        image_offsets_kernel<<<1, 1024, 0, ss>>>(d_kept, n_img, d_base, c->d_counters);
+        c->launches += 3;
+        c->sort_fast = true;
     } else {
         size_t t1 = c->cub_tmp_cap;
         iota_kernel<<<blocks, 256, 0, ss>>>(c->d_sort_idx, n_raw);
@@ -1014,14 +1099,26 @@ int run_gather(b200sift_ctx *c, int n_raw, int n_img, int dedupe, int convert, i
     if (n_raw <= 0) return 0;
     B200_CUDA(cudaStreamWaitEvent(c->stream, c->ev_side, 0));
     const int blocks = (n_raw + 255) / 256;
-    zero_out_counts_kernel<<<(n_img + 255) / 256, 256, 0, c->stream>>>(c->d_counters, n_img);
-    flag_kernel<<<blocks, 256, 0, c->stream>>>(c->d_raw, c->d_sort_idx, n_raw, dedupe, c->d_keep);
-    size_t t1 = c->cub_tmp_cap;
-    B200_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub_tmp, t1, c->d_keep, c->d_pos, n_raw, c->stream));
-    gather_kernel<<<(n_raw * 8 + 255) / 256, 256, 0, c->stream>>>(c->d_raw, with_desc ? c->d_raw_desc : nullptr,
-                                                                  c->d_sort_idx, c->d_keep, c->d_pos, n_raw, convert,
-                                                                  c->d_kps, c->d_desc, c->d_counters);
-    c->launches += 4;
+    if (c->sort_fast) {
+        // flags, in-image slots and per-image counts came out of the per-image sort (side stream)
+        if (dedupe != c->sort_dedupe) {
+            set_error("run_gather: dedupe flag differs from the one the sort was run with");
+            return B200SIFT_ESTATE;
+        }
+        gather_kernel<<<(n_raw * 8 + 255) / 256, 256, 0, c->stream>>>(
+            c->d_raw, with_desc ? c->d_raw_desc : nullptr, c->d_sort_idx, c->d_keep, c->d_pos, n_raw, convert, c->d_kps,
+            c->d_desc, c->d_counters, c->d_seg + 3 * (n_img + 1));
+        c->launches += 1;
+    } else {
+        zero_out_counts_kernel<<<(n_img + 255) / 256, 256, 0, c->stream>>>(c->d_counters, n_img);
+        flag_kernel<<<blocks, 256, 0, c->stream>>>(c->d_raw, c->d_sort_idx, n_raw, dedupe, c->d_keep);
+        size_t t1 = c->cub_tmp_cap;
+        B200_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub_tmp, t1, c->d_keep, c->d_pos, n_raw, c->stream));
+        gather_kernel<<<(n_raw * 8 + 255) / 256, 256, 0, c->stream>>>(
+            c->d_raw, with_desc ? c->d_raw_desc : nullptr, c->d_sort_idx, c->d_keep, c->d_pos, n_raw, convert, c->d_kps,
+            c->d_desc, c->d_counters, nullptr);
+        c->launches += 4;
+    }
     B200_CUDA(cudaGetLastError());
     const int n_cnt = CNT_HDR + n_img * CNT_PER_IMG;
     B200_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int32_t) * n_cnt, cudaMemcpyDeviceToHost,
@@ -1033,7 +1130,7 @@ int run_gather(b200sift_ctx *c, int n_raw, int n_img, int dedupe, int convert, i
 
 int run_sort_gather(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int dedupe, int convert, int with_desc)
 {
-    B200_CHECK(run_sort_async(c, n_raw, n_img, scan_order));
+    B200_CHECK(run_sort_async(c, n_raw, n_img, scan_order, dedupe));
     return run_gather(c, n_raw, n_img, dedupe, convert, with_desc);
 }
 
