@@ -22,6 +22,47 @@ void set_error(const char *fmt, ...)
 
 enum { CNT_CAND = 0, CNT_LOC = 1, CNT_RAW = 2, CNT_OUT = 3, CNT_HDR = 8, CNT_PER_IMG = 4 };
 
+namespace {
+struct TlMark {
+    cudaEvent_t ev;
+    std::string name;
+};
+std::vector<TlMark> g_tl;
+bool tl_on()
+{
+    static const bool on = getenv("B200SIFT_TIMELINE") != nullptr;
+    return on;
+}
+}  // namespace
+
+void tl_mark(cudaStream_t s, const char *fmt, ...)
+{
+    if (!tl_on()) return;
+    char buf[96];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    TlMark m;
+    cudaEventCreate(&m.ev);
+    cudaEventRecord(m.ev, s);
+    m.name = buf;
+    g_tl.push_back(m);
+}
+
+void tl_report()
+{
+    if (!tl_on() || g_tl.empty()) return;
+    cudaDeviceSynchronize();
+    for (size_t i = 0; i < g_tl.size(); ++i) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, g_tl[0].ev, g_tl[i].ev);
+        fprintf(stderr, "[b200sift timeline] %9.1f us  %s\n", ms * 1e3, g_tl[i].name.c_str());
+    }
+    for (auto &m : g_tl) cudaEventDestroy(m.ev);
+    g_tl.clear();
+}
+
 struct Timer {
     b200sift_ctx *c;
     explicit Timer(b200sift_ctx *ctx) : c(ctx) { cudaEventRecord(c->ev0, c->stream); }
@@ -191,6 +232,7 @@ void b200sift_destroy(b200sift_ctx *c)
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (c->h_counters) cudaFreeHost(c->h_counters);
+    if (c->h_pin) cudaFreeHost(c->h_pin);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     for (int o = 0; o < kMaxOctaves; ++o) cudaEventDestroy(c->ev_oct[o]);
@@ -298,9 +340,12 @@ int b200sift_detect_describe(b200sift_ctx *c, const b200sift_params *params, int
     Timer tm(c);
     static Trace tr;
     tr.mark(c, "start");
+    tl_mark(c->stream, "start");
     B200_CHECK(launch_gray_upsample(c, d_in, in_img_stride, d_ptrs, in_row_stride, n_images, h, w, channels, dtype, c->d_up,
                                     c->pyr.pitch[0]));
+    tl_mark(c->stream, "main  upsample");
     B200_CHECK(base_blur(c, c->d_up, sigma_diff));
+    tl_mark(c->stream, "main  base blur");
     tr.mark(c, "upsample+base blur");
     B200_CHECK(build_octaves(c, sig));
     tr.mark(c, "octaves (blur)");
@@ -310,11 +355,14 @@ int b200sift_detect_describe(b200sift_ctx *c, const b200sift_params *params, int
     const int n_raw = c->h_counters[CNT_RAW];
     B200_CHECK(run_sort_async(c, n_raw, n_images, 0, 1));         // side stream, overlaps the descriptors
     B200_CHECK(run_describe(c, P, c->d_raw, n_raw, 0, c->d_raw_desc));
+    tl_mark(c->stream, "main  describe");
     tr.mark(c, "describe (|| sort)");
     B200_CHECK(run_gather(c, n_raw, n_images, 1, 1, 1));
+    tl_mark(c->stream, "main  gather + counts on host");
     tr.mark(c, "dedupe+gather");
     tm.stop();
     tr.report();
+    tl_report();
     c->n_img_last = n_images;
     c->have_results = true;
     if (n_keypoints)
@@ -494,12 +542,22 @@ int b200sift_match_pairs(b200sift_ctx *c, int n_pairs, const int32_t *pairs, int
         B200_ARG(a >= 0 && a < c->n_img_last && b >= 0 && b < c->n_img_last);
     }
     Timer tm(c);
+    tl_mark(c->stream, "match start");
     B200_CHECK(run_match_pairs(c, n_pairs, pairs, desc_thresh, vote_thr));
-    std::vector<PairResult> res(n_pairs);
-    B200_CUDA(cudaMemcpyAsync(res.data(), c->d_pair_res, sizeof(PairResult) * n_pairs, cudaMemcpyDeviceToHost,
-                              c->stream));
+    tl_mark(c->stream, "main  pack + match + finalize");
+    if (c->h_pin_cap < sizeof(PairResult) * n_pairs) {  // pinned: a pageable target would stage the copy
+        if (c->h_pin) cudaFreeHost(c->h_pin);
+        c->h_pin = nullptr;
+        c->h_pin_cap = 0;
+        B200_CUDA(cudaMallocHost(&c->h_pin, sizeof(PairResult) * n_pairs * 2));
+        c->h_pin_cap = sizeof(PairResult) * n_pairs * 2;
+    }
+    PairResult *res = static_cast<PairResult *>(c->h_pin);
+    B200_CUDA(cudaMemcpyAsync(res, c->d_pair_res, sizeof(PairResult) * n_pairs, cudaMemcpyDeviceToHost, c->stream));
     tm.stop();
     B200_CUDA(cudaStreamSynchronize(c->stream));
+    tl_mark(c->stream, "main  pair results on host");
+    tl_report();
     c->pair_counts.assign(n_pairs, 0);
     for (int p = 0; p < n_pairs; ++p) {
         c->pair_counts[p] = res[p].n_matches;

@@ -10,6 +10,10 @@
 namespace b200 {
 
 void set_error(const char *fmt, ...);
+// B200SIFT_TIMELINE=1: tl_mark() records an event on `s` after whatever was just queued there;
+// tl_report() (end of detect_describe / match_pairs) prints all marks in microseconds since the first.
+void tl_mark(cudaStream_t s, const char *fmt, ...);
+void tl_report();
 
 #define B200_CUDA(call)                                                              \
     do {                                                                             \
@@ -116,6 +120,7 @@ struct b200sift_ctx {
     // sort overlaps the descriptor kernel (dependencies by events, no host involvement)
     cudaStream_t side_stream = nullptr;
     cudaStream_t blur_side_stream = nullptr;  // non-seeding layers of each octave (build_octaves)
+    void *h_pin = nullptr; size_t h_pin_cap = 0;  // pinned scratch for small device->host results
     bool sort_fast = false;                   // last run_sort_async took the per-image shared-memory path
     int sort_dedupe = 0;
     int pyr_o_tail = 0;                       // first octave produced by the pyramid tail kernel (0 = none)

@@ -950,6 +950,7 @@ int run_detect(b200sift_ctx *c, const b200sift_params &p, int /*want_scan_order*
                 extrema_rows_kernel<3><<<grid, 256, 0, es>>>(v, g, p.image_border_width, dp.dog_thresh, c->d_cand,
                                                             c->cand_cap, c->d_counters);
                 c->launches++;
+                tl_mark(es, "side  extrema oct %d..%d", o, o + g.n_oct - 1);
                 if (o >= o_merge) break;  // the group covered every remaining octave
             } else {
                 dim3 grid((sw + kExTW - 1) / kExTW, (sh + kExTH - 1) / kExTH, py.n_img);
@@ -969,14 +970,17 @@ int run_detect(b200sift_ctx *c, const b200sift_params &p, int /*want_scan_order*
             refine_kernel<<<blocks, 128, 0, c->stream>>>(v, dp, c->d_cand, c->cand_cap, c->d_loc, c->loc_cap,
                                                          c->d_counters);
             c->launches++;
+            tl_mark(c->stream, "main  refine");
             orient_kernel<<<c->sm_count * 5, kOriWarps * 32, 0, c->stream>>>(v, dp, c->d_loc, c->loc_cap, c->d_raw,
                                                                              c->raw_cap, c->d_counters);
             c->launches++;
+            tl_mark(c->stream, "main  orient");
         }
         B200_CUDA(cudaGetLastError());
         B200_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int32_t) * n_cnt, cudaMemcpyDeviceToHost,
                                   c->stream));
         B200_CUDA(cudaStreamSynchronize(c->stream));
+        tl_mark(c->stream, "main  counters on host");
         const int nc = c->h_counters[CNT_CAND], nl = c->h_counters[CNT_LOC], nr = c->h_counters[CNT_RAW];
         if (nc <= c->cand_cap && nl <= c->loc_cap && nr <= c->raw_cap) return 0;
         // a fixed-capacity list overflowed: grow to twice what was needed and redo the stage
@@ -1082,6 +1086,7 @@ int run_sort_async(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int de
         image_offsets_kernel<<<1, 1024, 0, ss>>>(d_kept, n_img, d_base, c->d_counters);
         c->launches += 3;
         c->sort_fast = true;
+        tl_mark(ss, "side  bucket + sort + offsets");
     } else {
         size_t t1 = c->cub_tmp_cap;
         iota_kernel<<<blocks, 256, 0, ss>>>(c->d_sort_idx, n_raw);

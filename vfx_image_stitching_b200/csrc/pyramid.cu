@@ -550,6 +550,7 @@ int build_octaves(b200sift_ctx *c, const double *sigmas)
             c->blur_stream = on_side ? c->blur_side_stream : nullptr;
             const int rc = launch_blur_set(c, p.layer(o, l - 1), p.layer(o, l), p.n_img, p.h[o], p.w[o], p.pitch[o],
                                            p.img_stride(o), R[l], l, dst2, h2, w2, pitch2, is2);
+            tl_mark(on_side ? c->blur_side_stream : c->stream, "%s oct %d layer %d", on_side ? "blur2" : "main ", o, l);
             c->blur_stream = nullptr;
             B200_CHECK(rc);
         }
@@ -568,6 +569,7 @@ int build_octaves(b200sift_ctx *c, const double *sigmas)
         pyramid_tail_kernel<<<p.n_img, kTailThreads, tail_smem, c->stream>>>(a);
         B200_CUDA(cudaGetLastError());
         c->launches++;
+        tl_mark(c->stream, "main  tail octaves %d..%d", o_tail, p.n_oct - 1);
         for (int o = o_tail; o < p.n_oct; ++o) B200_CUDA(cudaEventRecord(c->ev_oct[o], c->stream));
     }
     if (side_used) {  // later work on the main stream sees the whole pyramid
