@@ -20,21 +20,24 @@
 // 0.2 clip, renormalisation and round(512 v) of :512-524 with warp shuffles.
 #pragma once
 
-constexpr int kDescWarps = 4;
+constexpr int kDescWarps = 1;   // one warp per CTA: 13 CTAs (16.4 KB histogram + queue + 1 KB reserve each) fit an SM
 constexpr int kDescHistFloats = 128 * 32;
 constexpr int kDescU = 2;                       // surviving pixels evaluated per lane and batch
 constexpr int kDescQueue = 32 * kDescU + 32;
-constexpr size_t kDescSmemPerWarp = kDescHistFloats * sizeof(float) + 2 * kDescQueue * sizeof(int);
+constexpr size_t kDescSmemPerWarp = kDescHistFloats * sizeof(float) + kDescQueue * sizeof(int);
 
-__global__ void __launch_bounds__(kDescWarps * 32, 3)
+__global__ void __launch_bounds__(kDescWarps * 32, 13)
 describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw, int n, int converted,
                 uint8_t *__restrict__ desc_out, int32_t *__restrict__ work_counter)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float *hist = reinterpret_cast<float *>(dsm + (size_t)wib * kDescSmemPerWarp);
-    int *qx = reinterpret_cast<int *>(hist + kDescHistFloats);
-    int *qy = qx + kDescQueue;
+    // queue of surviving window offsets, packed (ys << 16) | (xs & 0xffff): |xs|, |ys| < 32768 because the
+    // window is clipped to the image and pyramid dimensions are below 32768
+    int *q = reinterpret_cast<int *>(hist + kDescHistFloats);
+    auto qx_of = [](int v) { return (v << 16) >> 16; };
+    auto qy_of = [](int v) { return v >> 16; };
     const int warps_total = gridDim.x * kDescWarps;
     constexpr int U = kDescU;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -181,19 +184,21 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
             const unsigned m = __ballot_sync(0xffffffffu, keep);
             if (keep) {
                 const int pos = qn + __popc(m & lt_mask);
-                qx[pos] = xs;
-                qy[pos] = ys;
+                q[pos] = (ys << 16) | (xs & 0xffff);
             }
             qn += __popc(m);
             __syncwarp();
             if (qn >= 32 * U) {
                 int sx[U], sy[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u) { sx[u] = qx[lane + 32 * u]; sy[u] = qy[lane + 32 * u]; }
-                const int tx = qx[lane + 32 * U], ty = qy[lane + 32 * U];
+                for (int u = 0; u < U; ++u) {
+                    const int e = q[lane + 32 * u];
+                    sx[u] = qx_of(e); sy[u] = qy_of(e);
+                }
+                const int te = q[lane + 32 * U];
                 __syncwarp();
                 qn -= 32 * U;
-                if (lane < qn) { qx[lane] = tx; qy[lane] = ty; }
+                if (lane < qn) q[lane] = te;
                 float ng[U][4];
                 gather4(sx, sy, ng);
                 if (pending) scatter2(px, py, all_live, pg);
@@ -216,8 +221,8 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
             for (int u = 0; u < U; ++u) {
                 live[u] = lane + 32 * u < qn;
                 // dead lanes gather queue entry 0 (a valid address when qn > 0) and drop the result
-                sx[u] = qn > 0 ? qx[live[u] ? lane + 32 * u : 0] : 0;
-                sy[u] = qn > 0 ? qy[live[u] ? lane + 32 * u : 0] : 0;
+                const int e = qn > 0 ? q[live[u] ? lane + 32 * u : 0] : 0;
+                sx[u] = qx_of(e); sy[u] = qy_of(e);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) ng[u][k] = 0.f;
             }

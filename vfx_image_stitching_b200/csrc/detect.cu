@@ -539,7 +539,9 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
                 const float mag = sqrtf(gx * gx + gy * gy);
                 const float ang = mod360f(atan2f(gy, gx) * B200_RAD2DEGF);
                 const float wgt = expf(weight_fac * (float)(dx * dx + dy * dy));
-                bin[u] = live[u] ? (int)rintf(ang * (float)nb / 360.f) % nb : -1;
+                int bi = (int)rintf(ang * (float)nb / 360.f);  // ang in [0, 360): bi in [0, nb]
+                if (bi >= nb) bi -= nb;                         // == bi % nb (:279)
+                bin[u] = live[u] ? bi : -1;
                 val[u] = wgt * mag;
             }
 #pragma unroll
@@ -548,9 +550,15 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
         }
         __syncwarp();
         for (int b = lane; b < nb; b += 32) {
-            double s = 0.0;
-            for (int l = 0; l < 32; ++l) s += hist[b][(l + lane) & 31];
-            raw_s[wib][b] = s;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // fixed order, 4 chains
+#pragma unroll
+            for (int l = 0; l < 32; l += 4) {
+                s0 += hist[b][(l + lane) & 31];
+                s1 += hist[b][(l + 1 + lane) & 31];
+                s2 += hist[b][(l + 2 + lane) & 31];
+                s3 += hist[b][(l + 3 + lane) & 31];
+            }
+            raw_s[wib][b] = (s0 + s1) + (s2 + s3);
         }
         __syncwarp();
         double mx = -1.0;
@@ -1005,10 +1013,16 @@ int run_describe(b200sift_ctx *c, const b200sift_params &p, const RawKeypoint *d
     static bool attr = false;
     if (!attr) {
         B200_CUDA(cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200_CUDA(cudaFuncSetAttribute(describe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr = true;
     }
     int blocks = (n + kDescWarps - 1) / kDescWarps;
-    if (blocks > c->sm_count * 3 * 4) blocks = c->sm_count * 3 * 4;
+    static int occ = 0;  // resident CTAs per SM (13 when the whole 228 KB carve-out is available)
+    if (!occ) {
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, describe_kernel, kDescWarps * 32, smem));
+        if (occ < 1) occ = 1;
+    }
+    if (blocks > c->sm_count * occ) blocks = c->sm_count * occ;
     B200_CHECK(ensure_counters(c, c->pyr.n_img > 0 ? c->pyr.n_img : 1));
     B200_CUDA(cudaMemsetAsync(c->d_counters + CNT_WORK_DESC, 0, sizeof(int32_t), c->stream));
     describe_kernel<<<blocks, kDescWarps * 32, smem, c->stream>>>(v, dp, d_raw, n, converted, d_out,
