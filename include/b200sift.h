@@ -117,8 +117,8 @@ B200SIFT_API int b200sift_get_keypoints(b200sift_ctx *ctx, int image, b200sift_k
 
 /* Same for ALL images of the last detect_describe in two device->host copies: kps / desc_u8 have
  * room for `capacity` records, image-major in batch order (image i starts at the sum of the
- * counts before it).  Either pointer may be NULL.  B200SIFT_EARG (nothing copied) when
- * capacity < sum(n_keypoints). */
+ * counts before it); images added with b200sift_append_results are not included.  Either pointer
+ * may be NULL.  B200SIFT_EARG (nothing copied) when capacity < sum(n_keypoints). */
 B200SIFT_API int b200sift_get_all_keypoints(b200sift_ctx *ctx, b200sift_keypoint *kps, uint8_t *desc_u8,
                                int64_t capacity);
 

@@ -364,6 +364,7 @@ int b200sift_detect_describe(b200sift_ctx *c, const b200sift_params *params, int
     tr.report();
     tl_report();
     c->n_img_last = n_images;
+    c->n_img_detected = n_images;
     c->have_results = true;
     if (n_keypoints)
         for (int i = 0; i < n_images; ++i) n_keypoints[i] = c->img_off[i + 1] - c->img_off[i];
@@ -410,7 +411,7 @@ int b200sift_get_all_keypoints(b200sift_ctx *c, b200sift_keypoint *kps, uint8_t 
         set_error("get_all_keypoints before a successful detect_describe");
         return B200SIFT_ESTATE;
     }
-    const int n = c->img_off.back();
+    const int n = c->img_off[c->n_img_detected];  // images appended later (append_results) are not part of it
     if (n == 0) return 0;
     if ((int64_t)n > capacity) {
         set_error("get_all_keypoints: capacity %lld < %d keypoints", (long long)capacity, n);

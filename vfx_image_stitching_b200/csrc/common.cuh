@@ -152,7 +152,8 @@ struct b200sift_ctx {
     int32_t *d_counters = nullptr; int32_t *h_counters = nullptr; int counters_len = 0;
     std::vector<int> img_off;      // n_img+1 prefix of final keypoints per image
     std::vector<int> stat_cand, stat_loc, stat_raw;
-    int n_img_last = 0;
+    int n_img_last = 0;     // images addressable by index: detected + appended
+    int n_img_detected = 0; // images of the last detect_describe (what get_all_keypoints returns)
     bool have_results = false;
 
     // matcher scratch
