@@ -8,6 +8,7 @@
 // INTER_NEAREST decimation), :100-111 generate_DoG_images.
 #include <math.h>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace b200 {
@@ -166,6 +167,7 @@ int launch_gray_upsample(b200sift_ctx *c, const void *d_in, size_t img_stride_by
 }
 
 #include "blur_strip.cuh"
+#include "blur_ring.cuh"
 
 // Generic tile blur: any radius <= kMaxBlurRadius, any (tiny) image.  32x32 output tile, halo tile in
 // shared memory, same arithmetic as the strip kernel.  All 256 threads of the CTA call it together.
@@ -407,6 +409,54 @@ static int launch_strip(b200sift_ctx *c, const float *src, float *dst, float *ds
     return 0;
 }
 
+template <int R>
+static int launch_ring(b200sift_ctx *c, const float *src, float *dst, float *dst2, int n_img, int h, int w,
+                       int pitch, size_t img_stride, int h2, int w2, int pitch2, size_t img_stride2, int tapset)
+{
+    const size_t smem = RingCfg<R>::smem;
+    static int occ = 0;  // resident CTAs per SM of this instantiation
+    if (!occ) {
+        B200_CUDA(cudaFuncSetAttribute(blur_ring_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B200_CUDA(cudaFuncSetAttribute(blur_ring_kernel<R>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blur_ring_kernel<R>, kRingThreads, smem));
+        if (occ < 1) occ = 1;
+    }
+    const int strips = (w + kRingW - 1) / kRingW;
+    const int cols = strips * n_img;
+    // One wave if possible (segments of >= 32 rows, all CTAs co-resident); larger problems run
+    // several waves of 128-row segments (y-halo re-read and re-filtered: 2R/128).
+    const int slots = c->sm_count * occ;
+    int n_seg = slots / cols;
+    int seg;
+    if (n_seg >= 1) {
+        seg = (h + n_seg - 1) / n_seg;
+        seg = ((seg + kRingBR - 1) / kRingBR) * kRingBR;
+        if (seg < 32) seg = 32;
+    } else {
+        seg = 128;
+    }
+    if (seg > 4096) seg = 4096;
+    dim3 grid(strips, (h + seg - 1) / seg, n_img);
+    BlurTaps<R> taps;
+    memcpy(taps.t, g_taps[c->device & 15].taps[tapset], sizeof(taps.t));
+    blur_ring_kernel<R><<<grid, kRingThreads, smem, c->blur_stream ? c->blur_stream : c->stream>>>(
+        src, dst, dst2, h, w, pitch, img_stride, h2, w2, pitch2, img_stride2, seg, taps);
+    c->launches++;
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// B200SIFT_BLUR=strip selects the scalar strip kernel (kept as a cross-check of the packed ring kernel).
+static bool use_ring_blur()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("B200SIFT_BLUR");
+        v = (e && !strcmp(e, "strip")) ? 0 : 1;
+    }
+    return v == 1;
+}
+
 static int launch_blur_set(b200sift_ctx *c, const float *src, float *dst, int n_img, int h, int w, int pitch,
                            size_t img_stride, int R, int tapset, float *dst2, int h2, int w2, int pitch2,
                            size_t img_stride2)
@@ -414,6 +464,21 @@ static int launch_blur_set(b200sift_ctx *c, const float *src, float *dst, int n_
     const bool strip_ok = (w >= 96) && (h >= 32) && (pitch % 4 == 0) &&
                           ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (img_stride % 4 == 0);
     if (strip_ok) {
+        if (use_ring_blur()) {
+            switch (R) {
+#define B200_RING(RR)                                                                                         \
+    case RR:                                                                                                  \
+        return launch_ring<RR>(c, src, dst, dst2, n_img, h, w, pitch, img_stride, h2, w2, pitch2, img_stride2, \
+                               tapset);
+                B200_RING(5)
+                B200_RING(6)
+                B200_RING(8)
+                B200_RING(10)
+                B200_RING(13)
+#undef B200_RING
+                default: break;
+            }
+        }
         switch (R) {
 #define B200_STRIP(RR)                                                                                         \
     case RR:                                                                                                   \
