@@ -10,6 +10,11 @@ restatement of the reference timed on the host cores.
 
 A "step" = one pass of the hot path over the 18-image set: detect+describe of every image
 (each image once) + brute-force matching and the translation vote of the 17 adjacent pairs.
+At N > 1 GPUs the job is a chain of N such sets (18 N images in pano order, 18 N - 1 adjacent
+pairs), sharded in contiguous blocks of 18 images per rank: per-GPU work is fixed ("weak"
+scaling), block-boundary pairs need the neighbour rank's first image (one all-gather).  The
+strong-scaling time of the single 18-image set over N ranks is reported next to it
+(`strong_18_images`).
 `value`  : inputs already resident in HBM, device-timed (CUDA events on the launch stream).
 `e2e`    : the same through the drop-in API with pinned HOST images in, host keypoints /
            descriptors / shifts out (H2D + D2H inside the timed region).
@@ -141,7 +146,7 @@ def reference_arm(args, rank):
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
-        'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': data,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': data,
         'config': {'workload': 'parrington 18 x 384x512 detect+describe + 17 adjacent-pair match + vote',
                    'note': 'the reference is pure Python (no compiled sources, oracle/_ref does not exist); this arm '
                            'times the C restatement oracle/sift_oracle.c on all host threads'},
@@ -186,13 +191,16 @@ def main():
     stream = torch.cuda.Stream(dev)
     ctx.set_stream(stream.cuda_stream)
 
-    imgs, data = load_workload()
-    n = len(imgs)
-    h, w = imgs[0].shape[:2]
+    base_imgs, data = load_workload()
+    nb = len(base_imgs)
+    h, w = base_imgs[0].shape[:2]
+    n = nb * world                                   # chain of `world` sets: weak scaling
     mpix_step = n * h * w / 1e6
-    pinned = [torch.from_numpy(im).pin_memory() for im in imgs]          # e2e inputs (host, pinned)
-    pinned_np = [t.numpy() for t in pinned]
-    resident = [t.to(dev) for t in pinned]                                # value-leg inputs (HBM)
+    pinned_base = [torch.from_numpy(im).pin_memory() for im in base_imgs]   # e2e inputs (host, pinned)
+    resident_base = [t.to(dev) for t in pinned_base]                        # value-leg inputs (HBM)
+    pinned_np = [pinned_base[i % nb].numpy() for i in range(n)]
+    resident = [resident_base[i % nb] for i in range(n)]
+    imgs = base_imgs
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     backend = panorama.GpuBackend(ctx)
     lo, hi = panorama.shard_range(n, rank, world)
@@ -257,11 +265,18 @@ def main():
     ms_dev, wall_dev, out_dev, launches = timed(step_resident, args.steps, args.warmup)
     ms_e2e, wall_e2e, out_e2e, _ = timed(step_e2e, args.steps, args.warmup)
     clocks = sampler.stop() if sampler else None
+    strong = None
+    if world > 1:   # the single 18-image set split over all ranks (strong scaling), for the record
+        def step_strong():
+            return panorama.sharded_panorama_shifts(resident_base, backend, dist=dist, device=dev)
+        ms_s, _, _, _ = timed(step_strong, max(3, args.steps // 2), 3)
+        strong = {'ms_per_step': ms_s, 'value': nb * h * w / 1e6 / (ms_s / 1e3), 'unit': UNIT,
+                  'sharding': '18 images in contiguous blocks over all ranks'}
 
     counts = np.asarray(out_e2e[1])
     desc_pairs = float(sum(int(counts[i]) * int(counts[i + 1]) for i in range(n - 1)))
-    h2d = sum(int(t.numel()) for t in pinned[lo:hi])
-    d2h = int(sum(int(c) for c in counts[lo:hi])) * (24 + 128) + (n - 1) * 16
+    h2d = n * int(pinned_base[0].numel())                                   # whole job, all ranks
+    d2h = int(counts.sum()) * (24 + 128) + (n - 1) * 16
 
     line = None
     if rank == 0:
@@ -272,15 +287,25 @@ def main():
         import ctypes as C
         detail = {}
         sig = sift_impl.generate_gaussian_kernels(1.6, 3)
+        t_sum = 0.0
         for name, s in [('base', 1.2489996)] + [(f'layer{l}', float(sig[l])) for l in range(1, 6)]:
             ms = C.c_float()
-            _capi.check(lib.b200sift_bench_blur(ctx.handle, n, 2 * h, 2 * w, s, 20, 1, C.byref(ms)))
-            by = 8.0 * n * (2 * h) * (2 * w)
+            _capi.check(lib.b200sift_bench_blur(ctx.handle, nb, 2 * h, 2 * w, s, 20, 1, C.byref(ms)))
+            by = 8.0 * nb * (2 * h) * (2 * w)
             detail[name] = {'sigma': round(s, 4), 'ms': ms.value, 'GB/s': by / ms.value / 1e6}
-        dom = detail['layer5']
-        roof = {'bound': 'hbm', 'kernel': 'blur_strip_kernel<13> (sigma 3.09, ksize 27)', 'achieved': dom['GB/s'],
-                'peak': peak, 'unit': 'GB/s', 'frac': dom['GB/s'] / peak, 'traffic': None,
-                'algorithmic_bytes_per_launch': 8 * n * 2 * h * 2 * w, 'peak_source': peak_src,
+            t_sum += ms.value
+        by = 8.0 * nb * (2 * h) * (2 * w)
+        ach = by / (t_sum / 6) / 1e6      # bytes per launch / average launch duration over the 6 blurs
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of blur_ring_kernel at this shape, from
+        # the ncu --set full capture summarised in profiles/r1_ring_blur_ncu.md (59.1-61.3 MB read +
+        # 10.7-12.6 MB written: the rest of the output is still dirty in L2 when the kernel ends)
+        traffic = {5: 70.9e6, 6: 70.9e6, 8: 70.6e6, 10: 70.7e6, 13: 73.9e6}
+        roof = {'bound': 'hbm', 'kernel': 'blur_ring_kernel<R> (octave-0 layer shape; average over the base blur '
+                                          'and the 5 layer blurs of one octave: R = 5, 5, 6, 8, 10, 13)',
+                'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
+                'traffic': sum(traffic[r] for r in (5, 5, 6, 8, 10, 13)) / 6,
+                'algorithmic_bytes_per_launch': 8 * nb * 2 * h * 2 * w, 'peak_source': peak_src,
+                'timing': 'each launch alone between CUDA events on the launch stream, 256 MiB L2 flush before it',
                 'per_sigma': detail}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -290,12 +315,13 @@ def main():
         line = {
             'metric': METRIC, 'value': mpix_step / (ms_dev / 1e3), 'unit': UNIT, 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev, 'higher_is_better': True,
-            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': data,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': data,
             'config': {'workload': 'parrington 18 x 384x512 detect+describe + 17 adjacent-pair match + vote '
-                                   '(BASELINE.json configs[1])',
+                                   '(BASELINE.json configs[1])' +
+                                   (f'; {world} such sets chained in pano order ({n} images, {n - 1} pairs)' if world > 1 else ''),
                        'images': n, 'pairs': n - 1, 'keypoints': int(counts.sum()),
-                       'sharding': f'images in contiguous blocks over {world} rank(s); pair (i,i+1) on the owner of i; '
-                                   'all-gather of block-first descriptors',
+                       'sharding': f'contiguous blocks of {nb} images per rank over {world} rank(s); pair (i,i+1) on the '
+                                   'owner of i; one all-gather of every block\'s first-image descriptors',
                        'l2': 'per-step pyramid working set ~0.47 GB > 126 MB L2; plus a 256 MiB flush write before '
                              'every timed step (outside the per-step CUDA events)'},
             'e2e': {'value': mpix_step / (ms_e2e / 1e3), 'unit': UNIT, 'ms_per_step': ms_e2e,
@@ -304,6 +330,8 @@ def main():
             'match_desc_pairs_per_s': desc_pairs / (ms_dev / 1e3), 'image_pairs_per_s': (n - 1) / (ms_dev / 1e3),
             'roofline': roof, 'cpu_baseline': cpu, 'clocks': clocks,
         }
+        if strong:
+            line['strong_18_images'] = strong
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -90,6 +90,10 @@ B200SIFT_API void b200sift_destroy(b200sift_ctx *ctx);
 /* Run all work of this context on `cuda_stream` (a cudaStream_t; NULL = the
  * context's own stream).  Lets a torch caller order work on its stream. */
 B200SIFT_API int b200sift_set_stream(b200sift_ctx *ctx, void *cuda_stream);
+
+/* The CUDA stream (cudaStream_t) the context currently launches on: its own, or the one given to
+ * b200sift_set_stream.  Lets a host framework order its own streams against the library's work. */
+B200SIFT_API int b200sift_get_stream(b200sift_ctx *ctx, void **cuda_stream);
 /* Device time in ms of the kernels of the last detect_describe / match call
  * (CUDA events on the context stream; host<->device copies excluded). */
 B200SIFT_API int b200sift_last_kernel_ms(b200sift_ctx *ctx, float *ms);
@@ -173,6 +177,30 @@ B200SIFT_API int b200sift_get_pair_matches(b200sift_ctx *ctx, int p, int32_t *ia
  * device pointers of this context's GPU.  *image_index receives the new image's index. */
 B200SIFT_API int b200sift_append_results(b200sift_ctx *ctx, const uint8_t *desc, const float *xy, int n,
                                          int on_device, int32_t *image_index);
+
+/* ---- multi-GPU neighbour exchange (the boundary pair of image_stitching_sift.py:312-327) ----
+ * Wire format: rows of 136 bytes.  Row 0 is a header of 34 int32: header[0] = keypoints of the image,
+ * header[1..n_tail] = caller-defined (copied from the host array `tail`, n_tail <= 33).  Rows 1..min(n, cap)
+ * hold one keypoint each: 128 descriptor bytes + (x, y) float32.
+ *
+ * pack: image `image` of the last detect_describe -> dst (device, (cap+1)*136 bytes).  Stream-ordered on the
+ * context stream; no host synchronisation. */
+B200SIFT_API int b200sift_pack_exchange(b200sift_ctx *ctx, int image, const int32_t *tail, int n_tail, void *dst,
+                                        int cap);
+
+/* unpack, after the all-gather: `gathered` (device) = `world` blocks of (cap+1)*136 bytes.  Copies the `world`
+ * headers to headers (host, world*34 int32; the one synchronisation of the exchange).  If src >= 0 and block
+ * src holds no more than cap keypoints, its rows are appended as an extra image exactly like
+ * b200sift_append_results and *image_index receives its index; otherwise *image_index = -1. */
+B200SIFT_API int b200sift_unpack_exchange(b200sift_ctx *ctx, const void *gathered, int world, int cap, int src,
+                                          int32_t *headers, int32_t *image_index);
+
+/* b200sift_match_pairs whose result stays on the device: the voted (dx, dy) of pair p is written as two
+ * doubles at dst + p*dst_stride bytes ((0,0) without matches) on the context stream, no host
+ * synchronisation, so that it can feed a collective directly.  b200sift_get_pair_matches is not available
+ * after this call. */
+B200SIFT_API int b200sift_match_pairs_device(b200sift_ctx *ctx, int n_pairs, const int32_t *pairs, int desc_thresh,
+                                             double dist_sq_thresh, void *dst, size_t dst_stride);
 
 /* ransac() translation vote (image_stitching_sift.py:86-111) on the device:
  * matches n x 4 float (xA,yA,xB,yB); returns the winning index in *best

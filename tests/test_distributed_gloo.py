@@ -18,8 +18,16 @@ def _free_port():
     return p
 
 
-class OracleBackend:
-    """The backend interface of panorama.py with the CPU oracle playing the kernels."""
+def _oracle_backend():
+    from vfx_image_stitching_b200.panorama import BackendBase
+
+    class OracleBackend(BackendBase, _OraclePrimitives):
+        pass
+    return OracleBackend()
+
+
+class _OraclePrimitives:
+    """The backend primitives of panorama.py with the CPU oracle playing the kernels."""
 
     def __init__(self):
         from oracle import sift_oracle as so
@@ -63,15 +71,18 @@ def _images():
     return panorama_set(5, 96, 128, seed=7, shift=(-2, -40))
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, min_rows=None):
     import sys
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, 'tests'))
     import torch.distributed as dist
+    from vfx_image_stitching_b200 import panorama
     from vfx_image_stitching_b200.panorama import sharded_panorama_shifts
+    if min_rows:
+        panorama.MIN_EXCHANGE_ROWS = min_rows   # forces the capacity-growth round of the exchange
     dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
     try:
-        shifts, counts = sharded_panorama_shifts(_images(), OracleBackend(), dist=dist, device='cpu')
+        shifts, counts = sharded_panorama_shifts(_images(), _oracle_backend(), dist=dist, device='cpu')
         q.put((rank, shifts, counts))
     finally:
         dist.destroy_process_group()
@@ -86,16 +97,16 @@ def test_shard_ranges():
         assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
 
 
-@pytest.mark.parametrize('world', [2, 3])
-def test_sharded_equals_single_process(world):
+@pytest.mark.parametrize('world,min_rows', [(2, None), (3, None), (2, 8)])
+def test_sharded_equals_single_process(world, min_rows):
     import torch.multiprocessing as mp
     from vfx_image_stitching_b200.panorama import sharded_panorama_shifts
-    ref_shifts, ref_counts = sharded_panorama_shifts(_images(), OracleBackend())
+    ref_shifts, ref_counts = sharded_panorama_shifts(_images(), _oracle_backend())
     assert len(ref_shifts) == 4 and sum(abs(abs(s[0]) - 40) < 1.0 and abs(abs(s[1]) - 2) < 1.0 for s in ref_shifts) >= 3
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, min_rows)) for r in range(world)]
     for p in procs:
         p.start()
     got = [q.get(timeout=90) for _ in range(world)]

@@ -1,0 +1,69 @@
+"""N = 2 on real GPUs (NCCL): the sharded first loop of run_panorama must return exactly what one
+process returns.  Needs two visible GPUs; skipped otherwise (the CPU/gloo twin of this test is
+tests/test_distributed_gloo.py)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _images(n=7):
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'parrington.npz'))['gray'][:n]
+    return [np.ascontiguousarray(np.repeat(im[:, :, None], 3, axis=2)) for im in g]
+
+
+def _worker(rank, world, port, q, min_rows):
+    import sys
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from vfx_image_stitching_b200 import _capi, panorama
+    if min_rows:
+        panorama.MIN_EXCHANGE_ROWS = min_rows   # forces the capacity-growth round of the exchange
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world, device_id=dev)
+    try:
+        backend = panorama.GpuBackend(_capi.default_context(rank))
+        out = None
+        for _ in range(2):   # second pass reuses the persistent exchange buffers
+            out = panorama.sharded_panorama_shifts(_images(), backend, dist=dist, device=dev)
+        q.put((rank, out[0], out[1]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('min_rows', [None, 64])
+def test_two_gpus_equal_one_process(min_rows):
+    torch = pytest.importorskip('torch')
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    from vfx_image_stitching_b200 import image_stitching_sift as iss
+    ref_shifts, ref_counts, _ = iss.panorama_shifts(_images(), return_details=True)
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, min_rows)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, shifts, counts in got:
+        assert counts == [int(c) for c in ref_counts], rank
+        assert shifts == [(float(a), float(b)) for a, b in ref_shifts], rank

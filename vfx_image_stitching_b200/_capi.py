@@ -44,6 +44,7 @@ PROTOTYPES = {
     'b200sift_create': (_i, [_i, _pp]),
     'b200sift_destroy': (None, [_vp]),
     'b200sift_set_stream': (_i, [_vp, _vp]),
+    'b200sift_get_stream': (_i, [_vp, _pp]),
     'b200sift_last_kernel_ms': (_i, [_vp, C.POINTER(C.c_float)]),
     'b200sift_launch_count': (_i, [_vp, C.POINTER(C.c_longlong)]),
     'b200sift_sync': (_i, [_vp]),
@@ -57,6 +58,9 @@ PROTOTYPES = {
     'b200sift_match_pairs': (_i, [_vp, _i, _ip, _i, _d, C.POINTER(C.c_double), _ip, _ip, _vp]),
     'b200sift_get_pair_matches': (_i, [_vp, _i, _vp, _vp, _vp]),
     'b200sift_append_results': (_i, [_vp, _vp, _vp, _i, _i, _ip]),
+    'b200sift_pack_exchange': (_i, [_vp, _i, _ip, _i, _vp, _i]),
+    'b200sift_unpack_exchange': (_i, [_vp, _vp, _i, _i, _i, _ip, _ip]),
+    'b200sift_match_pairs_device': (_i, [_vp, _i, _ip, _i, _d, _vp, _sz]),
     'b200sift_ransac': (_i, [_vp, _vp, _i, _d, C.POINTER(C.c_double), _ip]),
     'b200sift_gaussian_blur': (_i, [_vp, _vp, _i, _i, _d, _vp, _i]),
     'b200sift_base_image': (_i, [_vp, _vp, _i, _i, _d, _d, _vp]),
@@ -147,6 +151,12 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr):
         check(self.lib.b200sift_set_stream(self.handle, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def stream_handle(self):
+        """cudaStream_t (int) the context launches on."""
+        st = C.c_void_p()
+        check(self.lib.b200sift_get_stream(self.handle, C.byref(st)))
+        return st.value or 0
 
     def last_kernel_ms(self):
         ms = C.c_float()

@@ -255,6 +255,13 @@ int b200sift_set_stream(b200sift_ctx *c, void *s)
     return 0;
 }
 
+int b200sift_get_stream(b200sift_ctx *c, void **s)
+{
+    B200_ARG(c && s);
+    *s = (void *)c->stream;
+    return 0;
+}
+
 int b200sift_last_kernel_ms(b200sift_ctx *c, float *ms)
 {
     B200_ARG(c && ms);
@@ -588,6 +595,8 @@ int b200sift_get_pair_matches(b200sift_ctx *c, int p, int32_t *ia, int32_t *ib, 
     return 0;
 }
 
+static int grow_results(b200sift_ctx *c, int used, int need);
+
 int b200sift_append_results(b200sift_ctx *c, const uint8_t *desc, const float *xy, int n, int on_device,
                             int32_t *image_index)
 {
@@ -598,22 +607,7 @@ int b200sift_append_results(b200sift_ctx *c, const uint8_t *desc, const float *x
     }
     B200_CUDA(cudaSetDevice(c->device));
     const int used = c->img_off.back();
-    if (used + n > c->out_cap) {  // grow the compact result arrays, keeping their contents
-        const int ncap = used + n + (used + n) / 4 + 1024;
-        b200sift_keypoint *nk = nullptr;
-        uint8_t *nd = nullptr;
-        B200_CUDA(cudaMalloc((void **)&nk, sizeof(b200sift_keypoint) * (size_t)ncap));
-        B200_CUDA(cudaMalloc((void **)&nd, (size_t)ncap * 128));
-        B200_CUDA(cudaMemcpyAsync(nk, c->d_kps, sizeof(b200sift_keypoint) * (size_t)used, cudaMemcpyDeviceToDevice,
-                                  c->stream));
-        B200_CUDA(cudaMemcpyAsync(nd, c->d_desc, (size_t)used * 128, cudaMemcpyDeviceToDevice, c->stream));
-        B200_CUDA(cudaStreamSynchronize(c->stream));
-        cudaFree(c->d_kps);
-        cudaFree(c->d_desc);
-        c->d_kps = nk;
-        c->d_desc = nd;
-        c->out_cap = ncap;
-    }
+    B200_CHECK(grow_results(c, used, used + n));
     const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     if (n > 0) {
         B200_CUDA(cudaMemcpyAsync(c->d_desc + (size_t)used * 128, desc, (size_t)n * 128, kind, c->stream));
@@ -626,6 +620,171 @@ int b200sift_append_results(b200sift_ctx *c, const uint8_t *desc, const float *x
     *image_index = c->n_img_last;
     c->img_off.push_back(used + n);
     c->n_img_last += 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------ multi-GPU neighbour exchange
+namespace xchg {
+constexpr int kXRow = 136;   // bytes per wire row: 128 descriptor + 8 xy
+struct XHeader { int32_t v[34]; };
+
+__global__ void pack_exchange_kernel(const uint8_t *__restrict__ desc, const b200sift_keypoint *__restrict__ kps,
+                                     int n_rows, uint8_t *__restrict__ dst, const XHeader hdr)
+{
+    // one 8-byte word per thread: 17 words per row; row 0 = header
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = t / 17, wd = t - row * 17;
+    if (row > n_rows) return;
+    uint2 val;
+    if (row == 0) {
+        val = make_uint2((unsigned)hdr.v[2 * wd], (unsigned)hdr.v[2 * wd + 1]);
+    } else if (wd < 16) {
+        val = reinterpret_cast<const uint2 *>(desc + (size_t)(row - 1) * 128)[wd];
+    } else {
+        const b200sift_keypoint &k = kps[row - 1];
+        val = make_uint2(__float_as_uint(k.x), __float_as_uint(k.y));
+    }
+    reinterpret_cast<uint2 *>(dst + (size_t)row * kXRow)[wd] = val;
+}
+
+__global__ void unpack_exchange_kernel(const uint8_t *__restrict__ src, int n_rows, uint8_t *__restrict__ desc,
+                                       b200sift_keypoint *__restrict__ kps)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = t / 17, wd = t - row * 17;
+    if (row >= n_rows) return;
+    const uint2 val = reinterpret_cast<const uint2 *>(src + (size_t)(row + 1) * kXRow)[wd];
+    if (wd < 16) {
+        reinterpret_cast<uint2 *>(desc + (size_t)row * 128)[wd] = val;
+    } else {
+        b200sift_keypoint k;
+        k.x = __uint_as_float(val.x); k.y = __uint_as_float(val.y);
+        k.size = 0.f; k.angle = 0.f; k.response = 0.f; k.octave = 0;
+        kps[row] = k;
+    }
+}
+
+__global__ void pair_shifts_kernel(const PairResult *__restrict__ res, int n, uint8_t *__restrict__ dst, size_t stride)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    double *o = reinterpret_cast<double *>(dst + (size_t)p * stride);
+    const bool any = res[p].n_matches > 0;
+    o[0] = any ? res[p].dx : 0.0;
+    o[1] = any ? res[p].dy : 0.0;
+}
+
+}  // namespace xchg
+using namespace xchg;
+
+// grow the compact result arrays to hold `need` records, keeping their contents
+static int grow_results(b200sift_ctx *c, int used, int need)
+{
+    if (need <= c->out_cap) return 0;
+    const int ncap = need + need / 4 + 1024;
+    b200sift_keypoint *nk = nullptr;
+    uint8_t *nd = nullptr;
+    B200_CUDA(cudaMalloc((void **)&nk, sizeof(b200sift_keypoint) * (size_t)ncap));
+    B200_CUDA(cudaMalloc((void **)&nd, (size_t)ncap * 128));
+    B200_CUDA(cudaMemcpyAsync(nk, c->d_kps, sizeof(b200sift_keypoint) * (size_t)used, cudaMemcpyDeviceToDevice,
+                              c->stream));
+    B200_CUDA(cudaMemcpyAsync(nd, c->d_desc, (size_t)used * 128, cudaMemcpyDeviceToDevice, c->stream));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_kps);
+    cudaFree(c->d_desc);
+    c->d_kps = nk;
+    c->d_desc = nd;
+    c->out_cap = ncap;
+    return 0;
+}
+
+int b200sift_pack_exchange(b200sift_ctx *c, int image, const int32_t *tail, int n_tail, void *dst, int cap)
+{
+    B200_ARG(c && dst && cap >= 0 && n_tail >= 0 && n_tail <= 33 && (n_tail == 0 || tail));
+    if (!c->have_results) {
+        set_error("pack_exchange before a successful detect_describe");
+        return B200SIFT_ESTATE;
+    }
+    B200_ARG(image >= 0 && image < c->n_img_last);
+    B200_CUDA(cudaSetDevice(c->device));
+    const int off = c->img_off[image], n = c->img_off[image + 1] - off;
+    XHeader h;
+    memset(&h, 0, sizeof(h));
+    h.v[0] = n;
+    for (int i = 0; i < n_tail; ++i) h.v[1 + i] = tail[i];
+    const int rows = n < cap ? n : cap;
+    const int threads = (rows + 1) * 17;
+    pack_exchange_kernel<<<(threads + 255) / 256, 256, 0, c->stream>>>(c->d_desc + (size_t)off * 128, c->d_kps + off,
+                                                                        rows, static_cast<uint8_t *>(dst), h);
+    c->launches++;
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int b200sift_unpack_exchange(b200sift_ctx *c, const void *gathered, int world, int cap, int src, int32_t *headers,
+                             int32_t *image_index)
+{
+    B200_ARG(c && gathered && headers && image_index && world >= 1 && cap >= 0 && src < world);
+    if (!c->have_results) {
+        set_error("unpack_exchange before a successful detect_describe");
+        return B200SIFT_ESTATE;
+    }
+    B200_CUDA(cudaSetDevice(c->device));
+    *image_index = -1;
+    const size_t block = (size_t)(cap + 1) * kXRow;
+    const size_t need_pin = (size_t)world * kXRow;
+    if (c->h_pin_cap < need_pin) {
+        if (c->h_pin) cudaFreeHost(c->h_pin);
+        c->h_pin = nullptr;
+        c->h_pin_cap = 0;
+        B200_CUDA(cudaMallocHost(&c->h_pin, need_pin * 2));
+        c->h_pin_cap = need_pin * 2;
+    }
+    B200_CUDA(cudaMemcpy2DAsync(c->h_pin, kXRow, gathered, block, kXRow, world, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    memcpy(headers, c->h_pin, need_pin);
+    if (src < 0) return 0;
+    const int n = headers[(size_t)src * 34];
+    B200_ARG(n >= 0);
+    if (n > cap) return 0;  // truncated on the wire: the caller grows cap and repeats the exchange
+    const int used = c->img_off.back();
+    B200_CHECK(grow_results(c, used, used + n));
+    if (n > 0) {
+        const int threads = n * 17;
+        unpack_exchange_kernel<<<(threads + 255) / 256, 256, 0, c->stream>>>(
+            static_cast<const uint8_t *>(gathered) + (size_t)src * block, n, c->d_desc + (size_t)used * 128,
+            c->d_kps + used);
+        c->launches++;
+        B200_CUDA(cudaGetLastError());
+    }
+    *image_index = c->n_img_last;
+    c->img_off.push_back(used + n);
+    c->n_img_last += 1;
+    return 0;
+}
+
+int b200sift_match_pairs_device(b200sift_ctx *c, int n_pairs, const int32_t *pairs, int desc_thresh, double vote_thr,
+                                void *dst, size_t dst_stride)
+{
+    B200_ARG(c && n_pairs >= 0 && (n_pairs == 0 || (pairs && dst && dst_stride >= 2 * sizeof(double))));
+    if (!c->have_results) {
+        set_error("match_pairs_device before a successful detect_describe");
+        return B200SIFT_ESTATE;
+    }
+    c->pair_n = 0;
+    c->pair_counts.clear();
+    if (n_pairs == 0) return 0;
+    B200_CUDA(cudaSetDevice(c->device));
+    for (int p = 0; p < n_pairs; ++p) {
+        const int a = pairs[2 * p], b = pairs[2 * p + 1];
+        B200_ARG(a >= 0 && a < c->n_img_last && b >= 0 && b < c->n_img_last);
+    }
+    B200_CHECK(run_match_pairs(c, n_pairs, pairs, desc_thresh, vote_thr));
+    pair_shifts_kernel<<<(n_pairs + 127) / 128, 128, 0, c->stream>>>(c->d_pair_res, n_pairs, static_cast<uint8_t *>(dst),
+                                                                     dst_stride);
+    c->launches++;
+    B200_CUDA(cudaGetLastError());
+    c->pair_n = 0;  // match lists are not retrievable through get_pair_matches after this variant
     return 0;
 }
 

@@ -15,6 +15,14 @@ import ctypes as C
 
 import numpy as np
 
+MIN_EXCHANGE_ROWS = 4096   # initial row capacity of the first-image exchange (grown on demand)
+_prof = None   # debug hook: tools/profile_sharded.py sets a callable(name)
+
+
+def _mark(name):
+    if _prof is not None:
+        _prof(name)
+
 
 def shard_range(n_items, rank, world):
     """Contiguous block [lo, hi) of rank `rank`: 18 items over 8 ranks -> 3,3,2,2,2,2,2,2."""
@@ -23,7 +31,56 @@ def shard_range(n_items, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-class GpuBackend:
+ROW_BYTES = 136      # wire row of the exchange: 128 descriptor bytes + (x, y) float32
+HDR_INTS = 34        # row 0: [keypoints of the image, lo, block length, 0 ...]
+
+
+class BackendBase:
+    """What sharded_panorama_shifts needs from the compute side.
+
+    A backend implements the four primitives detect / first_image / append_remote / match_pairs;
+    the three exchange steps below are then provided with plain tensor operations (this is what
+    the gloo tests run, with the oracle as compute).  GpuBackend overrides the exchange steps with
+    single kernels of the C library."""
+
+    def pack_first(self, row, cap, tail, device):
+        """Fill `row` ((cap+1, 136) uint8 on `device`) with the header + the first local image."""
+        import torch
+        d, xy = self.first_image(device)
+        m = int(d.shape[0])
+        hdr = torch.zeros(HDR_INTS, dtype=torch.int32)
+        hdr[0] = m
+        for i, v in enumerate(tail):
+            hdr[1 + i] = int(v)
+        row[0].copy_(hdr.view(torch.uint8))
+        m = min(m, cap)
+        if m:
+            row[1:1 + m, :128].copy_(d[:m])
+            row[1:1 + m, 128:].copy_(xy[:m].contiguous().view(torch.uint8).view(m, 8))
+
+    def unpack(self, gathered, world, cap, src):
+        """-> (headers int32 (world, 34) on the host, local index of block `src` appended as an
+        extra image, or None when src < 0 or the block was truncated on the wire)."""
+        import torch
+        g3 = gathered.view(world, cap + 1, ROW_BYTES)
+        hdr = g3[:, 0, :].contiguous().cpu().view(torch.int32).numpy().reshape(world, HDR_INTS)
+        idx = None
+        if src >= 0 and int(hdr[src, 0]) <= cap:
+            m = int(hdr[src, 0])
+            r_desc = g3[src, 1:1 + m, :128].contiguous()
+            r_xy = g3[src, 1:1 + m, 128:].contiguous().view(torch.float32).view(m, 2)
+            idx = self.append_remote(r_desc, r_xy)
+        return hdr, idx
+
+    def match_pairs_into(self, pairs, ransac_thr, desc_thresh, res):
+        """Voted (dx, dy) of local pair p into res[p, 0:2] (float64 tensor on the exchange device)."""
+        import torch
+        if pairs:
+            sh = np.asarray(self.match_pairs(pairs, ransac_thr, desc_thresh), np.float64).reshape(-1, 2)
+            res[:len(pairs), :2].copy_(torch.from_numpy(sh))
+
+
+class GpuBackend(BackendBase):
     """CUDA kernels behind the C ABI; results of the local block stay in HBM."""
 
     def __init__(self, ctx=None):
@@ -40,7 +97,7 @@ class GpuBackend:
 
     def first_image(self, device):
         """(uint8 (n,128) descriptors, float32 (n,2) xy) of local image 0 as torch tensors on `device`
-        (zero-copy views of the context's buffers, copied once into fresh tensors)."""
+        (zero-copy views of the context's buffers)."""
         import torch
         from ._capi import check
         if len(self.counts) == 0 or self.counts[0] == 0:
@@ -53,9 +110,9 @@ class GpuBackend:
             def __init__(self, ptr, shape, typestr):
                 self.__cuda_array_interface__ = {'shape': shape, 'typestr': typestr, 'data': (ptr, False),
                                                  'version': 3, 'strides': None}
-        desc = torch.as_tensor(_View(d_desc.value, (n.value, 128), '|u1'), device=device).clone()
+        desc = torch.as_tensor(_View(d_desc.value, (n.value, 128), '|u1'), device=device)
         kps = torch.as_tensor(_View(d_kps.value, (n.value, 6), '<f4'), device=device)
-        return desc, kps[:, :2].contiguous()
+        return desc, kps[:, :2]
 
     def append_remote(self, desc, xy):
         """Make a gathered (remote) image matchable; returns its local image index."""
@@ -72,6 +129,50 @@ class GpuBackend:
         from . import image_stitching_sift as iss
         return iss.match_pairs(pairs, ransac_thr, desc_thresh, self.ctx)[0]
 
+    # ---- exchange steps as single library calls on the context stream (no torch ops, no host sync
+    # except the header read-back inside unpack)
+    def _sync_streams(self, device, before):
+        """The library works on the context stream, torch.distributed on torch's current stream."""
+        import torch
+        cur = torch.cuda.current_stream(device)
+        ext = torch.cuda.ExternalStream(self.ctx.stream_handle(), device=device)
+        if before:
+            ext.wait_stream(cur)
+        else:
+            cur.wait_stream(ext)
+
+    def pack_first(self, row, cap, tail, device):
+        from ._capi import check
+        t = (C.c_int32 * max(1, len(tail)))(*[int(v) for v in tail])
+        if len(self.counts) == 0:
+            return BackendBase.pack_first(self, row, cap, tail, device)   # empty block: header only
+        self._sync_streams(device, True)
+        check(self.ctx.lib.b200sift_pack_exchange(self.ctx.handle, 0, t, len(tail), C.c_void_p(row.data_ptr()), cap))
+        self._sync_streams(device, False)
+
+    def unpack(self, gathered, world, cap, src):
+        from ._capi import check
+        if len(self.counts) == 0:
+            return BackendBase.unpack(self, gathered, world, cap, -1)
+        hdr = np.zeros((world, HDR_INTS), np.int32)
+        idx = C.c_int32(-1)
+        self._sync_streams(gathered.device, True)
+        check(self.ctx.lib.b200sift_unpack_exchange(self.ctx.handle, C.c_void_p(gathered.data_ptr()), world, cap,
+                                                    src, hdr.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(idx)))
+        return hdr, (idx.value if idx.value >= 0 else None)
+
+    def match_pairs_into(self, pairs, ransac_thr, desc_thresh, res):
+        from ._capi import check
+        if not pairs:
+            return
+        pr = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1, 2))
+        self._sync_streams(res.device, True)
+        check(self.ctx.lib.b200sift_match_pairs_device(self.ctx.handle, len(pairs),
+                                                       pr.ctypes.data_as(C.POINTER(C.c_int32)), int(desc_thresh),
+                                                       float(ransac_thr), C.c_void_p(res.data_ptr()),
+                                                       res.stride(0) * res.element_size()))
+        self._sync_streams(res.device, False)
+
 
 def sharded_panorama_shifts(images, backend, ransac_thr=3, desc_thresh=25000, dist=None, device='cpu'):
     """All adjacent-pair shifts of `images` (every rank passes the same list; each rank only
@@ -84,58 +185,73 @@ def sharded_panorama_shifts(images, backend, ransac_thr=3, desc_thresh=25000, di
         rank, world = dist.get_rank(), dist.get_world_size()
     lo, hi = shard_range(n, rank, world)
     counts_local = np.asarray(backend.detect([images[i] for i in range(lo, hi)]), np.int64)
+    _mark('detect')
 
-    # ---- exchange: first image of every rank (one padded all-gather of descriptors + xy)
+    # ---- exchange: first image of every rank in ONE all-gather.  A keypoint travels as a 136-byte
+    # row (128 B descriptor + 8 B xy); row 0 is a header (count, lo, block length), so no separate
+    # count exchange is needed.  The row capacity is agreed implicitly: every rank sees every
+    # header, and if some count exceeds the current capacity all ranks grow it and repeat.
     remote_idx = None
     if world > 1:
-        first_d, first_xy = backend.first_image(device)
-        cnt = torch.tensor([first_d.shape[0], lo, hi - lo], dtype=torch.int32, device=device)
-        cnts = torch.zeros(world * 3, dtype=torch.int32, device=device)   # dim-0 concatenation
-        dist.all_gather_into_tensor(cnts, cnt)
-        cnts = cnts.cpu().numpy().reshape(world, 3)
-        cap = max(1, int(cnts[:, 0].max()))
-        # descriptors (128 B) and xy (8 B) of one keypoint travel in one 136-byte row
-        row = torch.zeros((cap, 136), dtype=torch.uint8, device=device)
-        if first_d.shape[0]:
-            row[:first_d.shape[0], :128] = first_d
-            row[:first_xy.shape[0], 128:] = first_xy.view(torch.uint8).reshape(-1, 8)
-        gathered = torch.zeros((world * cap, 136), dtype=torch.uint8, device=device)
-        dist.all_gather_into_tensor(gathered, row)       # the one data-path collective
-        gathered = gathered.view(world, cap, 136)
-        if hi > lo and hi < n:   # my last image's right neighbour lives on another rank
-            src = int(np.nonzero((cnts[:, 1] == hi) & (cnts[:, 2] > 0))[0][0])
-            m = int(cnts[src, 0])
-            r_desc = gathered[src, :m, :128].contiguous()
-            r_xy = gathered[src, :m, 128:].contiguous().view(torch.float32).reshape(m, 2)
-            remote_idx = backend.append_remote(r_desc, r_xy)
+        st = getattr(backend, '_xchg', None)
+        if st is None or st['world'] != world or st['device'] != str(device):
+            st = backend._xchg = {'world': world, 'device': str(device), 'cap': 0}
+        cap = max(st['cap'], MIN_EXCHANGE_ROWS)
+        # blocks are contiguous and empty blocks only occur at the tail, so the owner of image `hi`
+        # is simply the next rank
+        src = rank + 1 if (hi > lo and hi < n) else -1
+        while True:
+            if st['cap'] != cap:
+                st['cap'] = cap
+                st['row'] = torch.zeros((cap + 1, ROW_BYTES), dtype=torch.uint8, device=device)
+                st['all'] = torch.zeros((world * (cap + 1), ROW_BYTES), dtype=torch.uint8, device=device)
+            backend.pack_first(st['row'], cap, (lo, hi - lo), device)
+            _mark('x.pack')
+            dist.all_gather_into_tensor(st['all'], st['row'])       # the one data-path collective
+            _mark('x.gather')
+            hdr, remote_idx = backend.unpack(st['all'], world, cap, src)
+            need = int(hdr[:, 0].max())
+            if need <= cap:
+                break
+            cap = 1 << (need - 1).bit_length()               # same decision on every rank
+        cnts = hdr[:, :3]
+        _mark('exchange')
     else:
         cnts = np.array([[0, lo, hi - lo]])
 
-    # ---- owned pairs, one batched device pass
-    pairs, owners = [], []
+    # ---- owned pairs in one batched device pass, results to every rank (tiny): per image
+    # (dx, dy, keypoint count)
+    pairs = []
     for i in range(lo, hi):
-        if i + 1 >= n:
-            continue
-        pairs.append((i - lo, i + 1 - lo) if i + 1 < hi else (i - lo, remote_idx))
-        owners.append(i)
-    my = np.zeros((max(hi - lo, 0), 3), np.float64)
-    if hi > lo:
-        my[:, 2] = counts_local
-    if pairs:
-        for i, s in zip(owners, backend.match_pairs(pairs, ransac_thr, desc_thresh)):
-            my[i - lo, 0], my[i - lo, 1] = s
-
-    # ---- results to every rank (tiny): per-image (dx, dy, keypoint count)
+        if i + 1 < n:
+            pairs.append((i - lo, i + 1 - lo) if i + 1 < hi else (i - lo, remote_idx))
     if world > 1:
         maxb = max(1, int(cnts[:, 2].max()))
-        buf = torch.zeros((maxb, 3), dtype=torch.float64, device=device)
+        if st.get('maxb') != maxb:
+            st['maxb'] = maxb
+            st['res_h'] = torch.zeros((maxb, 3), dtype=torch.float64)
+            st['out_h'] = torch.zeros((world * maxb, 3), dtype=torch.float64)
+            if torch.device(device).type == 'cuda':
+                st['res_h'], st['out_h'] = st['res_h'].pin_memory(), st['out_h'].pin_memory()
+            st['res_d'] = torch.zeros((maxb, 3), dtype=torch.float64, device=device)
+            st['out_d'] = torch.zeros((world * maxb, 3), dtype=torch.float64, device=device)
+        st['res_h'].zero_()
         if hi > lo:
-            buf[:hi - lo] = torch.from_numpy(my).to(device)
-        out = torch.zeros((world * maxb, 3), dtype=torch.float64, device=device)
-        dist.all_gather_into_tensor(out, buf)
-        out = out.cpu().numpy().reshape(world, maxb, 3)
+            st['res_h'][:hi - lo, 2] = torch.from_numpy(counts_local.astype(np.float64))
+        st['res_d'].copy_(st['res_h'], non_blocking=True)
+        backend.match_pairs_into(pairs, ransac_thr, desc_thresh, st['res_d'])
+        _mark('match')
+        dist.all_gather_into_tensor(st['out_d'], st['res_d'])
+        st['out_h'].copy_(st['out_d'])                      # synchronous: the results are on the host now
+        out = st['out_h'].numpy().reshape(world, maxb, 3)
         rows = np.concatenate([out[r, :int(cnts[r, 2])] for r in range(world)], 0)
     else:
-        rows = my
+        rows = np.zeros((max(hi - lo, 0), 3), np.float64)
+        if hi > lo:
+            rows[:, 2] = counts_local
+        if pairs:
+            for p, sft in enumerate(backend.match_pairs(pairs, ransac_thr, desc_thresh)):
+                rows[p, 0], rows[p, 1] = sft
+    _mark('results')
     shifts = [(float(rows[i, 0]), float(rows[i, 1])) for i in range(n - 1)]
     return shifts, rows[:, 2].astype(np.int64).tolist()
