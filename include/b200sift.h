@@ -263,6 +263,21 @@ B200SIFT_API int b200sift_extrema_candidates(b200sift_ctx *ctx, const b200sift_p
 B200SIFT_API int b200sift_cylindrical_projection(b200sift_ctx *ctx, const uint8_t *src, int h, int w, int ch,
                                     double focal, uint8_t *dst);
 
+/* blend_two_images (image_stitching_sift.py:156-202, with pad_image :139-153) on the device: imgA / imgB are
+ * host uint8 BGR images (h x w x 3), (dx, dy) the shift and ref_match = {xA, yA, xB, yB} the matched pair
+ * compute_shift_sift returned.  *out_h / *out_w receive the size of the result; with out == NULL the call
+ * only reports that size.  alpha_float64 = 0 reproduces the reference CLI (ref_match holds Python floats,
+ * numpy blends in float32), 1 the float64 arithmetic numpy uses when ref_match holds numpy float64 scalars. */
+B200SIFT_API int b200sift_blend_two_images(b200sift_ctx *ctx, const uint8_t *imgA, int hA, int wA,
+                                           const uint8_t *imgB, int hB, int wB, double dx, double dy,
+                                           const double *ref_match, int alpha_float64, uint8_t *out,
+                                           size_t out_capacity, int32_t *out_h, int32_t *out_w);
+
+/* The reduction of rectangle_crop (image_stitching_sift.py:224-236): box = {y_min, y_max, x_min, x_max} of the
+ * pixels whose cv2 BGR2GRAY value exceeds black_threshold; y_max = -1 when there is none. */
+B200SIFT_API int b200sift_crop_bbox(b200sift_ctx *ctx, const uint8_t *img, int h, int w, int black_threshold,
+                                    int32_t *box);
+
 /* Measurement hook for the roofline line of bench.py: runs `iters` launches of
  * the Gaussian blur kernel for `sigma` on an internal n_img x h x w float32
  * batch (pitch = w rounded up to 8) that is already resident in HBM, and

@@ -315,3 +315,115 @@ def cylindrical_projection(img_bgr, focal_len):
     lib().orc_cylindrical_projection(img.ctypes.data_as(C.c_void_p), h, w, ch, float(focal_len),
                                      out.ctypes.data_as(C.c_void_p))
     return out
+
+
+# ----------------------------------------------------------------------------- f4: the step after the path
+def read_pano_data(pano_file_path):
+    """image_stitching_sift.py:12-46: a line naming a .jpg/.png, followed (not necessarily directly)
+    by a line without blanks that parses as float, yields (path, focal)."""
+    images, focuses, pending = [], [], None
+    with open(pano_file_path, 'r', encoding='utf-8') as f:
+        lines = f.read().splitlines()
+    for text in lines:
+        low = text.strip().lower()
+        if '.jpg' in low or '.png' in low:
+            pending = text.strip()
+        elif ' ' not in low and len(low) > 0:
+            try:
+                val = float(low)
+            except ValueError:
+                continue
+            if pending is not None:
+                images.append(pending)
+                focuses.append(val)
+                pending = None
+    return images, focuses
+
+
+def pad_image(img_bgr, move_x, move_y):
+    """image_stitching_sift.py:139-153: zero padding in front for a non-negative move, behind otherwise."""
+    mx, my = int(round(move_x)), int(round(move_y))
+    h, w = img_bgr.shape[:2]
+    out = np.zeros((h + abs(my), w + abs(mx), 3), img_bgr.dtype)
+    oy, ox = max(my, 0), max(mx, 0)
+    out[oy:oy + h, ox:ox + w] = img_bgr
+    return out
+
+
+def blend_two_images(shift_vec, ref_match, imgA, imgB):
+    """image_stitching_sift.py:156-202, vectorised over columns.  The dtype of alpha follows numpy's
+    promotion: a Python float (the reference CLI: ref_match holds kp.pt tuples) blends in float32,
+    a numpy float64 scalar in float64."""
+    dx, dy = shift_vec
+    if dx < 0:
+        dx, dy = -dx, -dy
+        ref_match = (ref_match[1], ref_match[0])
+        imgA, imgB = imgB, imgA
+    padA_x = imgB.shape[1] - imgA.shape[1] + ref_match[0][0] - ref_match[1][0]
+    padB_x = ref_match[0][0] - ref_match[1][0]
+    overlap_range = ref_match[1][0] - ref_match[0][0] + imgA.shape[1]
+    shiftA = pad_image(imgA, -padA_x, -dy)
+    shiftB = pad_image(imgB, padB_x, dy)
+    HH, WW = max(shiftA.shape[0], shiftB.shape[0]), max(shiftA.shape[1], shiftB.shape[1])
+    canvasA = np.zeros((HH, WW, 3), np.float32)
+    canvasB = np.zeros((HH, WW, 3), np.float32)
+    canvasA[:shiftA.shape[0], :shiftA.shape[1]] = shiftA
+    canvasB[:shiftB.shape[0], :shiftB.shape[1]] = shiftB
+    anyA = (canvasA != 0).any(axis=(0, 2))
+    anyB = (canvasB != 0).any(axis=(0, 2))
+    both = anyA & anyB
+    counter = np.cumsum(both) - both                      # overlap_counter before column cc
+    strong = isinstance(overlap_range, np.floating)       # numpy scalar -> float64 arithmetic
+    result = np.zeros((HH, WW, 3), np.float32)
+    onlyA, onlyB = anyA & ~anyB, anyB & ~anyA
+    result[:, onlyA] = canvasA[:, onlyA]
+    result[:, onlyB] = canvasB[:, onlyB]
+    if both.any():
+        alpha = (counter[both] / float(overlap_range)) if overlap_range != 0 else np.zeros(int(both.sum()))
+        if strong:
+            a64 = alpha.astype(np.float64)[None, :, None]
+            result[:, both] = ((1 - a64) * canvasA[:, both].astype(np.float64)
+                               + a64 * canvasB[:, both].astype(np.float64)).astype(np.float32)
+        else:
+            wa = (1.0 - alpha).astype(np.float32)[None, :, None]
+            wb = alpha.astype(np.float32)[None, :, None]
+            result[:, both] = wa * canvasA[:, both] + wb * canvasB[:, both]
+    # astype(np.uint8): the C cast (truncate, wrap modulo 256 for out-of-range values)
+    return result.astype(np.int32).astype(np.uint8)
+
+
+def rectangle_crop(img, black_threshold, extra_margin):
+    """image_stitching_sift.py:208-247."""
+    h, w = img.shape[:2]
+    gray = bgr2gray(img)
+    ys, xs = np.where(gray > black_threshold)
+    if ys.size == 0:
+        return img
+    y_min, y_max, x_min, x_max = ys.min(), ys.max(), xs.min(), xs.max()
+    y_min = max(0, y_min + extra_margin)
+    y_max = min(h - 1, y_max - extra_margin)
+    if y_min > y_max or x_min > x_max:
+        return img
+    return img[y_min:y_max + 1, x_min:x_max + 1]
+
+
+def drift_corrected_shifts(shift_list, n_images):
+    """image_stitching_sift.py:336-365: every dy loses the average drift final_dy / (N - 1)."""
+    acc = [(0, 0)]
+    for i in range(len(shift_list)):
+        acc.append((acc[i][0] + shift_list[i][0], acc[i][1] + shift_list[i][1]))
+    average_drift = acc[-1][1] / (n_images - 1) if n_images > 1 else 0
+    return [(dx, dy - average_drift) for dx, dy in shift_list]
+
+
+def stitch(cyl_imgs, shift_list, matched_pairs):
+    """Second loop of run_panorama (image_stitching_sift.py:367-381) + the default crop (:383-384)."""
+    new_shifts = drift_corrected_shifts(shift_list, len(cyl_imgs))
+    mosaic = cyl_imgs[0].copy()
+    for i in range(1, len(cyl_imgs)):
+        img = cyl_imgs[i]
+        diff_y = mosaic.shape[0] - img.shape[0]
+        if diff_y != 0:
+            img = pad_image(img, 0, diff_y)
+        mosaic = blend_two_images(new_shifts[i - 1], matched_pairs[i - 1], mosaic, img)
+    return mosaic

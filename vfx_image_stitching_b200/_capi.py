@@ -61,6 +61,9 @@ PROTOTYPES = {
     'b200sift_pack_exchange': (_i, [_vp, _i, _ip, _i, _vp, _i]),
     'b200sift_unpack_exchange': (_i, [_vp, _vp, _i, _i, _i, _ip, _ip]),
     'b200sift_match_pairs_device': (_i, [_vp, _i, _ip, _i, _d, _vp, _sz]),
+    'b200sift_blend_two_images': (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _d, _d, C.POINTER(C.c_double), _i, _vp, _sz,
+                                        _ip, _ip]),
+    'b200sift_crop_bbox': (_i, [_vp, _vp, _i, _i, _i, _ip]),
     'b200sift_ransac': (_i, [_vp, _vp, _i, _d, C.POINTER(C.c_double), _ip]),
     'b200sift_gaussian_blur': (_i, [_vp, _vp, _i, _i, _d, _vp, _i]),
     'b200sift_base_image': (_i, [_vp, _vp, _i, _i, _d, _d, _vp]),

@@ -22,6 +22,7 @@ SOURCES = {
     'detect.cu': ['--fmad=false'],
     'match.cu': [],
     'match_tc.cu': [],
+    'stitch.cu': ['--fmad=false'],
     'api.cu': [],
 }
 

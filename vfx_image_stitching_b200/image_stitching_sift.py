@@ -142,3 +142,157 @@ def match_pairs(pairs, ransac_thr=3, desc_thresh=25000, ctx=None):
     bp = [((float(xy[p, 0]), float(xy[p, 1])), (float(xy[p, 2]), float(xy[p, 3]))) if nm[p] else None
           for p in range(n)]
     return shifts, nm, best, bp
+
+
+# ----------------------------------------------------------------------------- f4: after the path
+def read_pano_data(pano_file_path):
+    """image_stitching_sift.py:12-46 -> (image paths, focal lengths) of an AutoStitch pano.txt.
+
+    Host logic: a line naming a .jpg / .png opens an entry, the next blank-free line that parses
+    as a float closes it; everything else (sizes, matrices, blank lines) is skipped."""
+    images, focuses = [], []
+    pending = None
+    with open(pano_file_path, 'r', encoding='utf-8') as fh:
+        for raw in fh.read().splitlines():
+            token = raw.strip()
+            low = token.lower()
+            if '.jpg' in low or '.png' in low:
+                pending = token
+                continue
+            if not low or ' ' in low:
+                continue
+            try:
+                focal = float(low)
+            except ValueError:
+                continue
+            if pending is not None:
+                images.append(pending)
+                focuses.append(focal)
+                pending = None
+    return images, focuses
+
+
+def pad_image(img_bgr, move_x, move_y):
+    """image_stitching_sift.py:139-153: translate by zero padding (rounded to whole pixels)."""
+    mx, my = int(round(move_x)), int(round(move_y))
+    img = np.asarray(img_bgr)
+    h, w = img.shape[:2]
+    out = np.zeros((h + abs(my), w + abs(mx), 3), img.dtype)
+    out[max(my, 0):max(my, 0) + h, max(mx, 0):max(mx, 0) + w] = img
+    return out
+
+
+def blend_two_images(shift_vec, ref_match, imgA, imgB, ctx=None):
+    """image_stitching_sift.py:156-202 on the GPU: imgB joined to imgA with a column-wise linear
+    cross-fade over the overlap.  Bit-identical to the reference, including numpy's choice of
+    float32 arithmetic when ref_match holds Python floats (the CLI) and float64 when it holds numpy
+    float64 scalars."""
+    ctx = ctx or default_context()
+    a = np.ascontiguousarray(imgA, np.uint8)
+    b = np.ascontiguousarray(imgB, np.uint8)
+    if a.ndim != 3 or b.ndim != 3 or a.shape[2] != 3 or b.shape[2] != 3:
+        raise ValueError('blend_two_images needs two H x W x 3 images')
+    strong = int(any(isinstance(v, np.floating) for p in ref_match for v in p))
+    rm = (C.c_double * 4)(float(ref_match[0][0]), float(ref_match[0][1]), float(ref_match[1][0]),
+                          float(ref_match[1][1]))
+    oh, ow = C.c_int32(), C.c_int32()
+    args = (ctx.handle, ptr(a), a.shape[0], a.shape[1], ptr(b), b.shape[0], b.shape[1], float(shift_vec[0]),
+            float(shift_vec[1]), rm, strong)
+    check(ctx.lib.b200sift_blend_two_images(*args, None, 0, C.byref(oh), C.byref(ow)))
+    out = np.empty((oh.value, ow.value, 3), np.uint8)
+    check(ctx.lib.b200sift_blend_two_images(*args, ptr(out), out.nbytes, C.byref(oh), C.byref(ow)))
+    return out
+
+
+def rectangle_crop(img, black_threshold, extra_margin, ctx=None):
+    """image_stitching_sift.py:208-247: crop to the bounding box of the pixels brighter than
+    black_threshold (grey value of cv2.cvtColor), trimmed by extra_margin at the top and bottom."""
+    ctx = ctx or default_context()
+    im = np.asarray(img)
+    src = np.ascontiguousarray(im, np.uint8)
+    h, w = src.shape[:2]
+    box = (C.c_int32 * 4)()
+    check(ctx.lib.b200sift_crop_bbox(ctx.handle, ptr(src), h, w, int(black_threshold), box))
+    y_min, y_max, x_min, x_max = (int(v) for v in box)
+    if y_max < 0:
+        return img
+    y_min = max(0, y_min + extra_margin)
+    y_max = min(h - 1, y_max - extra_margin)
+    if y_min > y_max or x_min > x_max:
+        return img
+    return im[y_min:y_max + 1, x_min:x_max + 1]
+
+
+def drift_corrected_shifts(shift_list, n_images):
+    """image_stitching_sift.py:336-365: remove the accumulated vertical drift, spread evenly."""
+    total_dy = 0
+    for _, dy in shift_list:
+        total_dy = total_dy + dy
+    average_drift = total_dy / (n_images - 1) if n_images > 1 else 0
+    return [(dx, dy - average_drift) for dx, dy in shift_list]
+
+
+def stitch_panorama(cyl_imgs, ransac_thr=3, desc_thresh=25000, margin=15, ctx=None):
+    """Both loops of run_panorama (image_stitching_sift.py:312-384) on already projected images:
+    adjacent-pair shifts (every image detected once, pairs matched on the device), drift
+    correction, chained blends, crop.  Returns (result, mosaic, shift_list, matched_pairs)."""
+    ctx = ctx or default_context()
+    imgs = [np.asarray(im) for im in cyl_imgs]
+    for i in range(len(imgs) - 1):                      # :318-320 equalise heights pairwise
+        diff_y = imgs[i].shape[0] - imgs[i + 1].shape[0]
+        if diff_y != 0:
+            imgs[i + 1] = pad_image(imgs[i + 1], 0, diff_y)
+    same = all(im.shape == imgs[0].shape for im in imgs)
+    if same and len(imgs) > 1:
+        sift_impl.detect_and_describe_batch(imgs, ctx=ctx, download=False)
+        shift_list, _, _, matched_pairs = match_pairs([(i, i + 1) for i in range(len(imgs) - 1)], ransac_thr,
+                                                      desc_thresh, ctx)
+    else:
+        shift_list, matched_pairs = [], []
+        for i in range(len(imgs) - 1):
+            s, p = compute_shift_sift(imgs[i], imgs[i + 1], ransac_thr, desc_thresh)
+            shift_list.append(s)
+            matched_pairs.append(p)
+    new_shifts = drift_corrected_shifts(shift_list, len(imgs))
+    mosaic = imgs[0].copy()
+    for i in range(1, len(imgs)):
+        nxt = imgs[i]
+        diff_y = mosaic.shape[0] - nxt.shape[0]
+        if diff_y != 0:
+            nxt = pad_image(nxt, 0, diff_y)
+        mosaic = blend_two_images(new_shifts[i - 1], matched_pairs[i - 1], mosaic, nxt, ctx=ctx)
+    return rectangle_crop(mosaic, 0, margin, ctx=ctx), mosaic, shift_list, matched_pairs
+
+
+def run_panorama(folder_path=None, pano_file=None, margin=None, save=True):
+    """image_stitching_sift.py:253-389.  With no arguments it asks the same three questions as the
+    reference; passing them makes the run non-interactive.  Returns the cropped panorama (and writes
+    <folder>/panoroma_sift.jpg like the reference when `save`)."""
+    import os
+    import cv2
+    if folder_path is None:
+        folder_path = input('image folder (default .): ').strip()
+    folder_path = folder_path or '.'
+    if not folder_path.endswith(('/', '\\')):
+        folder_path += '/'
+    if pano_file is None:
+        pano_file = input('pano.txt path (default <folder>/pano.txt): ').strip()
+    pano_file = pano_file or folder_path + 'pano.txt'
+    img_paths, focals = read_pano_data(pano_file)
+    if not img_paths:
+        print('no usable entries in', pano_file)
+        return None
+    cyl = []
+    for p, f in zip(img_paths, focals):
+        full = p if os.path.exists(p) else os.path.join(folder_path, os.path.basename(p.replace('\\', '/')))
+        img = cv2.imread(full)
+        if img is None:
+            raise FileNotFoundError(full)
+        cyl.append(cylindrical_projection(img, f))
+    if margin is None:
+        m = input('crop margin (default 15): ').strip()
+        margin = int(m) if m.isdigit() else 15
+    result, _, _, _ = stitch_panorama(cyl, margin=int(margin))
+    if save:
+        cv2.imwrite(os.path.join(folder_path, 'panoroma_sift.jpg'), result)
+    return result
