@@ -62,6 +62,22 @@ def test_blur_matches_oracle_and_cv2(si, oracle, shape):
         assert err < 2e-4 and err_cv < 2e-4
 
 
+def test_blur_ring_edges_and_determinism(si, oracle):
+    """The packed ring kernel's border patch, partial last strip / last batch and its mbarrier
+    hand-off: widths and heights around the 256-column strip, the 8-row batch and the 4-float chunk;
+    every result must repeat bit for bit (a race between the producer and consumer warps would not)."""
+    rng = np.random.default_rng(99)
+    for h, w in [(32, 96), (33, 97), (39, 255), (40, 256), (41, 257), (64, 259), (47, 511), (130, 513),
+                 (257, 770), (96, 1026)]:
+        img = (rng.random((h, w)) * 255).astype(np.float32)
+        for s in (1.2262735, 2.452547, 3.0900156):
+            got = si.gaussian_blur(img, s)
+            ref = oracle.gaussian_blur(img, s, 'c')
+            assert np.abs(got - ref).max() < 2e-4, (h, w, s)
+            for _ in range(3):
+                assert np.array_equal(si.gaussian_blur(img, s), got), (h, w, s)
+
+
 def test_base_image_bit_exact_upsample(si, oracle):
     g = natural_image(120, 90, 1)
     got = si.generate_base_image(g.astype(np.float32), 1.6, 0.5)

@@ -38,7 +38,7 @@ constexpr int kRingW = 256;      // strip width (columns)
 constexpr int kRingBR = 8;       // rows per batch
 constexpr int kRingThreads = 256;   // warps 0-3: fill + row pass, warps 4-7: column pass
 
-template <int R>
+template <int R, int STAGES>
 struct RingCfg {
     static constexpr int E4 = ((R + (R & 1)) + 3) & ~3;       // x halo per side, floats (multiple of 4, >= R + (R odd))
     static constexpr int INW = kRingW + 2 * E4;                // staged floats per input row
@@ -48,7 +48,7 @@ struct RingCfg {
     static constexpr int NV = (2 * E4 + 8) / 4;                // chunks a lane loads per tile in the row pass
     static constexpr int Q = (2 * R + kRingBR - 1) / kRingBR;  // batches the column pass lags behind the row pass
     static constexpr int NS = Q + 2;                           // ring slots (8 rows each)
-    static constexpr int S = (R >= 12) ? 2 : 3;                // input stages (cp.async ring)
+    static constexpr int S = STAGES;                           // input stages (cp.async ring): 2 or 3
     static constexpr size_t smem = (size_t)(S * kRingBR * INP + NS * kRingBR * TWP) * sizeof(float);
 };
 
@@ -79,13 +79,13 @@ __device__ __forceinline__ void ring_mbar_wait(unsigned long long *bar, unsigned
         : "memory");
 }
 
-template <int R>
+template <int R, int STAGES>
 __global__ void __launch_bounds__(kRingThreads)
 blur_ring_kernel(const float *__restrict__ src, float *__restrict__ dst, float *__restrict__ dst2, int h, int w,
                  int pitch, size_t img_stride, int h2, int w2, int pitch2, size_t img_stride2, int seg_rows,
                  const __grid_constant__ BlurTaps<R> taps)
 {
-    using C = RingCfg<R>;
+    using C = RingCfg<R, STAGES>;
     constexpr int TW = kRingW, BR = kRingBR, S = C::S, E4 = C::E4, INW = C::INW, INP = C::INP, TWP = C::TWP;
     constexpr int NCH = C::NCH, NV = C::NV, NS = C::NS, Q = C::Q;
     constexpr int STG = BR * INP;   // floats per input stage

@@ -409,41 +409,74 @@ static int launch_strip(b200sift_ctx *c, const float *src, float *dst, float *ds
     return 0;
 }
 
-template <int R>
-static int launch_ring(b200sift_ctx *c, const float *src, float *dst, float *dst2, int n_img, int h, int w,
-                       int pitch, size_t img_stride, int h2, int w2, int pitch2, size_t img_stride2, int tapset)
+template <int R, int STAGES>
+static int ring_occupancy(int *occ_out)
 {
-    const size_t smem = RingCfg<R>::smem;
     static int occ = 0;  // resident CTAs per SM of this instantiation
     if (!occ) {
-        B200_CUDA(cudaFuncSetAttribute(blur_ring_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        B200_CUDA(cudaFuncSetAttribute(blur_ring_kernel<R>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blur_ring_kernel<R>, kRingThreads, smem));
+        const size_t smem = RingCfg<R, STAGES>::smem;
+        B200_CUDA(cudaFuncSetAttribute(blur_ring_kernel<R, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+        B200_CUDA(cudaFuncSetAttribute(blur_ring_kernel<R, STAGES>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blur_ring_kernel<R, STAGES>, kRingThreads, smem));
         if (occ < 1) occ = 1;
     }
-    const int strips = (w + kRingW - 1) / kRingW;
-    const int cols = strips * n_img;
-    // One wave if possible (segments of >= 32 rows, all CTAs co-resident); larger problems run
-    // several waves of 128-row segments (y-halo re-read and re-filtered: 2R/128).
-    const int slots = c->sm_count * occ;
-    int n_seg = slots / cols;
-    int seg;
-    if (n_seg >= 1) {
-        seg = (h + n_seg - 1) / n_seg;
-        seg = ((seg + kRingBR - 1) / kRingBR) * kRingBR;
-        if (seg < 32) seg = 32;
-    } else {
-        seg = 128;
-    }
-    if (seg > 4096) seg = 4096;
-    dim3 grid(strips, (h + seg - 1) / seg, n_img);
+    *occ_out = occ;
+    return 0;
+}
+
+template <int R, int STAGES>
+static int launch_ring_s(b200sift_ctx *c, const float *src, float *dst, float *dst2, int n_img, int h, int w,
+                         int pitch, size_t img_stride, int h2, int w2, int pitch2, size_t img_stride2, int tapset,
+                         int seg)
+{
+    int occ;
+    B200_CHECK((ring_occupancy<R, STAGES>(&occ)));
+    dim3 grid((w + kRingW - 1) / kRingW, (h + seg - 1) / seg, n_img);
     BlurTaps<R> taps;
     memcpy(taps.t, g_taps[c->device & 15].taps[tapset], sizeof(taps.t));
-    blur_ring_kernel<R><<<grid, kRingThreads, smem, c->blur_stream ? c->blur_stream : c->stream>>>(
+    blur_ring_kernel<R, STAGES><<<grid, kRingThreads, RingCfg<R, STAGES>::smem,
+                                  c->blur_stream ? c->blur_stream : c->stream>>>(
         src, dst, dst2, h, w, pitch, img_stride, h2, w2, pitch2, img_stride2, seg, taps);
     c->launches++;
     B200_CUDA(cudaGetLastError());
     return 0;
+}
+
+// Grid shape.  A CTA marches down `seg` rows of one 256-column strip and re-filters 8*ceil(2R/8) halo
+// rows per segment, so segments should be long -- but a small problem must still fill the machine:
+//   * ONE wave when floor(slots / strip-columns) segments per column fill >= 80 % of the resident CTA
+//     slots (the 18-image pyramid octaves): every CTA is resident at once;
+//   * otherwise several waves of 256-row segments (halo work 2R/256).
+// Three input stages (two batches in flight per CTA) except for R = 13, whose 48-row ring leaves room
+// for two.  Two stages for R <= 8 would fit a fourth CTA per SM but measured 4-8 % slower
+// (8 x 6144 x 8192, 256-row segments: 564 vs 523 us at R = 5).
+template <int R>
+static int launch_ring(b200sift_ctx *c, const float *src, float *dst, float *dst2, int n_img, int h, int w,
+                       int pitch, size_t img_stride, int h2, int w2, int pitch2, size_t img_stride2, int tapset)
+{
+    constexpr int SDEEP = (R >= 12) ? 2 : 3;
+    int occ_deep = 1;
+    B200_CHECK((ring_occupancy<R, SDEEP>(&occ_deep)));
+    const int cols = ((w + kRingW - 1) / kRingW) * n_img;
+    const int slots = c->sm_count * occ_deep;
+    const int n1 = slots / cols;
+    int seg = 0;
+    bool one_wave = false;
+    if (n1 >= 1) {
+        seg = (h + n1 - 1) / n1;
+        seg = ((seg + kRingBR - 1) / kRingBR) * kRingBR;
+        if (seg < 32) seg = 32;
+        const int ctas = cols * ((h + seg - 1) / seg);
+        one_wave = ctas * 10 >= slots * 8 || h <= 256;
+    }
+    if (!one_wave) seg = 256;
+    {
+        static const char *e = getenv("B200SIFT_RING_SEG");  // experiment hook: force the segment height
+        if (e && atoi(e) >= 8) seg = (atoi(e) + 7) & ~7;
+    }
+    return launch_ring_s<R, SDEEP>(c, src, dst, dst2, n_img, h, w, pitch, img_stride, h2, w2, pitch2, img_stride2,
+                                   tapset, seg);
 }
 
 // B200SIFT_BLUR=strip selects the scalar strip kernel (kept as a cross-check of the packed ring kernel).
