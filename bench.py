@@ -300,13 +300,21 @@ def main():
         # the ncu --set full capture summarised in profiles/r1_ring_blur_ncu.md (59.1-61.3 MB read +
         # 10.7-12.6 MB written: the rest of the output is still dirty in L2 when the kernel ends)
         traffic = {5: 70.9e6, 6: 70.9e6, 8: 70.6e6, 10: 70.7e6, 13: 73.9e6}
+        # the same kernel where the layer no longer fits one wave of CTAs (the 4096x3072-frame regime of
+        # BASELINE.json configs[3]: 8 frames, octave-0 layers of 6144 x 8192): it is HBM-bound there
+        large = {}
+        for name, s in [('layer1', float(sig[1])), ('layer3', float(sig[3])), ('layer5', float(sig[5]))]:
+            ms = C.c_float()
+            _capi.check(lib.b200sift_bench_blur(ctx.handle, 8, 6144, 8192, s, 5, 1, C.byref(ms)))
+            large[name] = {'sigma': round(s, 4), 'ms': ms.value, 'GB/s': 8.0 * 8 * 6144 * 8192 / ms.value / 1e6,
+                           'frac': 8.0 * 8 * 6144 * 8192 / ms.value / 1e6 / peak}
         roof = {'bound': 'hbm', 'kernel': 'blur_ring_kernel<R> (octave-0 layer shape; average over the base blur '
                                           'and the 5 layer blurs of one octave: R = 5, 5, 6, 8, 10, 13)',
                 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
                 'traffic': sum(traffic[r] for r in (5, 5, 6, 8, 10, 13)) / 6,
                 'algorithmic_bytes_per_launch': 8 * nb * 2 * h * 2 * w, 'peak_source': peak_src,
                 'timing': 'each launch alone between CUDA events on the launch stream, 256 MiB L2 flush before it',
-                'per_sigma': detail}
+                'per_sigma': detail, 'large_shape_8x6144x8192': large}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             v, ms_cpu, sample, threads, dps = cpu_run(imgs, 1, 1, budget_s=40.0)

@@ -445,9 +445,9 @@ static int launch_ring_s(b200sift_ctx *c, const float *src, float *dst, float *d
 
 // Grid shape.  A CTA marches down `seg` rows of one 256-column strip and re-filters 8*ceil(2R/8) halo
 // rows per segment, so segments should be long -- but a small problem must still fill the machine:
-//   * ONE wave when floor(slots / strip-columns) segments per column fill >= 80 % of the resident CTA
-//     slots (the 18-image pyramid octaves): every CTA is resident at once;
-//   * otherwise several waves of 256-row segments (halo work 2R/256).
+//   * 256-row segments (halo work 2R/256) whenever they give at least one full wave of CTAs;
+//   * otherwise ONE wave: floor(slots / strip-columns) segments per column, at least 32 rows each (the
+//     18-image pyramid octaves: 432 CTAs on 444 slots, 128-row segments).
 // Three input stages (two batches in flight per CTA) except for R = 13, whose 48-row ring leaves room
 // for two.  Two stages for R <= 8 would fit a fourth CTA per SM but measured 4-8 % slower
 // (8 x 6144 x 8192, 256-row segments: 564 vs 523 us at R = 5).
@@ -461,16 +461,12 @@ static int launch_ring(b200sift_ctx *c, const float *src, float *dst, float *dst
     const int cols = ((w + kRingW - 1) / kRingW) * n_img;
     const int slots = c->sm_count * occ_deep;
     const int n1 = slots / cols;
-    int seg = 0;
-    bool one_wave = false;
-    if (n1 >= 1) {
+    int seg = 256;
+    if (n1 >= 1 && (long long)cols * ((h + 255) / 256) < slots) {  // 256-row segments would not even fill one wave
         seg = (h + n1 - 1) / n1;
         seg = ((seg + kRingBR - 1) / kRingBR) * kRingBR;
         if (seg < 32) seg = 32;
-        const int ctas = cols * ((h + seg - 1) / seg);
-        one_wave = ctas * 10 >= slots * 8 || h <= 256;
     }
-    if (!one_wave) seg = 256;
     {
         static const char *e = getenv("B200SIFT_RING_SEG");  // experiment hook: force the segment height
         if (e && atoi(e) >= 8) seg = (atoi(e) + 7) & ~7;
