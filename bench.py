@@ -297,7 +297,7 @@ def main():
         by = 8.0 * nb * (2 * h) * (2 * w)
         ach = by / (t_sum / 6) / 1e6      # bytes per launch / average launch duration over the 6 blurs
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of blur_ring_kernel at this shape, from
-        # the ncu --set full capture summarised in profiles/r1_ring_blur_ncu.md (59.1-61.3 MB read +
+        # the ncu --set full capture summarised in profiles/r1_final_ring_small_ncu.txt (59.1-61.3 MB read +
         # 10.7-12.6 MB written: the rest of the output is still dirty in L2 when the kernel ends)
         traffic = {5: 70.9e6, 6: 70.9e6, 8: 70.6e6, 10: 70.7e6, 13: 73.9e6}
         # the same kernel where the layer no longer fits one wave of CTAs (the 4096x3072-frame regime of
