@@ -23,7 +23,8 @@
 constexpr int kDescWarps = 1;   // one warp per CTA: 13 CTAs (16.4 KB histogram + queue + 1 KB reserve each) fit an SM
 constexpr int kDescHistFloats = 128 * 32;
 constexpr int kDescU = 2;                       // surviving pixels evaluated per lane and batch
-constexpr int kDescQueue = 32 * kDescU + 32;
+constexpr int kDescQueue = 32 * kDescU + 32 + 4;   // also the row table of the interval path (<= 96 rows + sentinel)
+constexpr int kDescMaxRows = 96;
 constexpr size_t kDescSmemPerWarp = kDescHistFloats * sizeof(float) + kDescQueue * sizeof(int);
 
 __global__ void __launch_bounds__(kDescWarps * 32, 13)
@@ -166,6 +167,103 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
         const int clo = max(ptx - half_w, 1), chi = min(ptx + half_w, cols - 2);
         const int nx = chi - clo + 1, ny = rhi - rlo + 1;
         const int total = (ok && nx > 0 && ny > 0) ? nx * ny : 0;
+        // ---- which window pixels pass the float32 pre-filter (the rotated 4x4 grid, :429-430)?
+        // For a fixed row the filter  |x*sin + y*cos| < lim && |x*cos - y*sin| < lim  holds on an
+        // INTERVAL of x (each term is monotone in x, also after float32 rounding), so the survivors
+        // are enumerated row by row instead of testing every pixel and compacting with ballots: a
+        // lane derives the interval of its rows analytically, widens it by two pixels and shrinks it
+        // with the very predicate the per-pixel test used -- the survivor set and its row-major order
+        // are exactly those of the per-pixel scan (kept below for windows taller than the row table).
+        auto keep_px = [&](int xs, float fy) -> bool {
+            const float fx = (float)xs;
+            return (fabsf(fx * sin_f + fy * cos_f) < lim) && (fabsf(fx * cos_f - fy * sin_f) < lim);
+        };
+        if (total > 0 && ny <= kDescMaxRows && total < 32768) {
+            const int xmin = clo - ptx, xmax = chi - ptx;
+            int T = 0;  // survivors so far (warp-uniform)
+            for (int r0 = 0; r0 < ny; r0 += 32) {
+                const int r = r0 + lane;
+                int a = 0, cnt = 0;
+                if (r < ny) {
+                    const float fy = (float)(rlo + r - pty);
+                    float xl = (float)xmin, xh = (float)xmax;
+                    bool none = false;
+                    const float b1 = fy * cos_f, b2 = -(fy * sin_f);
+                    if (fabsf(sin_f) > 1e-6f) {
+                        const float t0 = (-lim - b1) / sin_f, t1 = (lim - b1) / sin_f;
+                        xl = fmaxf(xl, fminf(t0, t1));
+                        xh = fminf(xh, fmaxf(t0, t1));
+                    } else if (!(fabsf(b1) < lim + 1.f)) {
+                        none = true;
+                    }
+                    if (fabsf(cos_f) > 1e-6f) {
+                        const float t0 = (-lim - b2) / cos_f, t1 = (lim - b2) / cos_f;
+                        xl = fmaxf(xl, fminf(t0, t1));
+                        xh = fminf(xh, fmaxf(t0, t1));
+                    } else if (!(fabsf(b2) < lim + 1.f)) {
+                        none = true;
+                    }
+                    int b = -1;
+                    if (!none && xl <= xh + 4.f) {
+                        a = max(xmin, (int)floorf(xl) - 2);
+                        b = min(xmax, (int)ceilf(xh) + 2);
+                        while (a <= b && !keep_px(a, fy)) ++a;
+                        while (b >= a && !keep_px(b, fy)) --b;
+                    } else {
+                        a = 0;
+                    }
+                    cnt = b >= a ? b - a + 1 : 0;
+                }
+                int incl = cnt;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += t;
+                }
+                if (r < ny) q[r] = ((T + incl - cnt) << 16) | (a & 0xffff);
+                T += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) q[ny] = T << 16;  // sentinel: every item index is below it
+            __syncwarp();
+            // items in batches of 32*U, lane <-> item base + lane + 32u (the assignment of the queue path);
+            // the gather of a batch is issued before the previous batch is evaluated
+            int rw[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) rw[u] = 0;
+            int px[U], py[U];
+            float pg[U][4];
+            bool plive[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) { px[u] = 0; py[u] = 0; plive[u] = false; }
+            bool pending = false;  // warp-uniform
+            for (int base = 0; base < T; base += 32 * U) {
+                int sx[U], sy[U];
+                bool live[U];
+                float ng[U][4];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = base + lane + 32 * u;
+                    live[u] = i < T;
+                    const int it = live[u] ? i : 0;   // dead lanes gather item 0 (valid address) and drop it
+                    int r = live[u] ? rw[u] : 0;
+                    while ((q[r + 1] >> 16) <= it) ++r;   // rows without survivors have equal starts
+                    if (live[u]) rw[u] = r;
+                    const int e = q[r];
+                    sx[u] = ((e << 16) >> 16) + (it - (e >> 16));
+                    sy[u] = rlo + r - pty;
+                }
+                gather4(sx, sy, ng);
+                if (pending) scatter2(px, py, plive, pg);
+                pending = true;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    px[u] = sx[u]; py[u] = sy[u]; plive[u] = live[u];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) pg[u][k] = ng[u][k];
+                }
+            }
+            if (pending) scatter2(px, py, plive, pg);
+        } else {
         int yy = lane / max(nx, 1), xx = lane - yy * max(nx, 1);
         int qn = 0;  // warp-uniform queue length
         int px[U], py[U];  // batch whose gather is in flight
@@ -229,6 +327,7 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
             if (qn > 0) gather4(sx, sy, ng);
             if (pending) scatter2(px, py, all_live, pg);
             if (qn > 0) scatter2(sx, sy, live, ng);
+        }
         }
         __syncwarp();
 
