@@ -24,7 +24,7 @@ constexpr int kDescWarps = 1;   // one warp per CTA: 13 CTAs (16.4 KB histogram 
 constexpr int kDescHistFloats = 128 * 32;
 constexpr int kDescU = 2;                       // surviving pixels evaluated per lane and batch
 constexpr int kDescQueue = 32 * kDescU + 32 + 4;   // also the row table of the interval path (<= 96 rows + sentinel)
-constexpr int kDescMaxRows = 96;
+constexpr int kDescMaxRows = 95;   // + 5 sentinel entries
 constexpr size_t kDescSmemPerWarp = kDescHistFloats * sizeof(float) + kDescQueue * sizeof(int);
 
 __global__ void __launch_bounds__(kDescWarps * 32, 13)
@@ -223,7 +223,7 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
                 if (r < ny) q[r] = ((T + incl - cnt) << 16) | (a & 0xffff);
                 T += __shfl_sync(0xffffffffu, incl, 31);
             }
-            if (lane == 0) q[ny] = T << 16;  // sentinel: every item index is below it
+            if (lane < 5) q[ny + lane] = T << 16;  // sentinels: every item index is below them
             __syncwarp();
             // items in batches of 32*U, lane <-> item base + lane + 32u (the assignment of the queue path);
             // the gather of a batch is issued before the previous batch is evaluated
@@ -246,7 +246,15 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
                     live[u] = i < T;
                     const int it = live[u] ? i : 0;   // dead lanes gather item 0 (valid address) and drop it
                     int r = live[u] ? rw[u] : 0;
-                    while ((q[r + 1] >> 16) <= it) ++r;   // rows without survivors have equal starts
+                    // advance to the row that holds item `it`: starts are non-decreasing (rows without
+                    // survivors have equal starts), so the number of the next four starts that are <= it
+                    // is the number of rows to skip; four independent loads instead of a dependent chain
+                    for (;;) {
+                        const int s1 = q[r + 1] >> 16, s2 = q[r + 2] >> 16, s3 = q[r + 3] >> 16, s4 = q[r + 4] >> 16;
+                        const int adv = (s1 <= it) + (s2 <= it) + (s3 <= it) + (s4 <= it);
+                        r += adv;
+                        if (adv < 4) break;
+                    }
                     if (live[u]) rw[u] = r;
                     const int e = q[r];
                     sx[u] = ((e << 16) >> 16) + (it - (e >> 16));
