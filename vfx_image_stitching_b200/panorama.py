@@ -43,6 +43,11 @@ class BackendBase:
     the gloo tests run, with the oracle as compute).  GpuBackend overrides the exchange steps with
     single kernels of the C library."""
 
+    def stream_ctx(self, device):
+        """Context manager under which the exchange (tensor operations + collectives) runs."""
+        import contextlib
+        return contextlib.nullcontext()
+
     def pack_first(self, row, cap, tail, device):
         """Fill `row` ((cap+1, 136) uint8 on `device`) with the header + the first local image."""
         import torch
@@ -129,26 +134,23 @@ class GpuBackend(BackendBase):
         from . import image_stitching_sift as iss
         return iss.match_pairs(pairs, ransac_thr, desc_thresh, self.ctx)[0]
 
-    # ---- exchange steps as single library calls on the context stream (no torch ops, no host sync
-    # except the header read-back inside unpack)
-    def _sync_streams(self, device, before):
-        """The library works on the context stream, torch.distributed on torch's current stream."""
+    # ---- exchange steps as single library calls.  The whole exchange -- these kernels, the tensor
+    # copies and both NCCL collectives -- runs on the CONTEXT's stream (torch.distributed issues on the
+    # current torch stream), so no events or cross-stream waits are needed; the only host
+    # synchronisations are the header read-back inside unpack and the final result download.
+    def stream_ctx(self, device):
         import torch
-        cur = torch.cuda.current_stream(device)
-        ext = torch.cuda.ExternalStream(self.ctx.stream_handle(), device=device)
-        if before:
-            ext.wait_stream(cur)
-        else:
-            cur.wait_stream(ext)
+        h = self.ctx.stream_handle()
+        if getattr(self, '_ext', None) is None or self._ext[0] != h:
+            self._ext = (h, torch.cuda.ExternalStream(h, device=device))
+        return torch.cuda.stream(self._ext[1])
 
     def pack_first(self, row, cap, tail, device):
         from ._capi import check
         t = (C.c_int32 * max(1, len(tail)))(*[int(v) for v in tail])
         if len(self.counts) == 0:
             return BackendBase.pack_first(self, row, cap, tail, device)   # empty block: header only
-        self._sync_streams(device, True)
         check(self.ctx.lib.b200sift_pack_exchange(self.ctx.handle, 0, t, len(tail), C.c_void_p(row.data_ptr()), cap))
-        self._sync_streams(device, False)
 
     def unpack(self, gathered, world, cap, src):
         from ._capi import check
@@ -156,7 +158,6 @@ class GpuBackend(BackendBase):
             return BackendBase.unpack(self, gathered, world, cap, -1)
         hdr = np.zeros((world, HDR_INTS), np.int32)
         idx = C.c_int32(-1)
-        self._sync_streams(gathered.device, True)
         check(self.ctx.lib.b200sift_unpack_exchange(self.ctx.handle, C.c_void_p(gathered.data_ptr()), world, cap,
                                                     src, hdr.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(idx)))
         return hdr, (idx.value if idx.value >= 0 else None)
@@ -166,12 +167,10 @@ class GpuBackend(BackendBase):
         if not pairs:
             return
         pr = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1, 2))
-        self._sync_streams(res.device, True)
         check(self.ctx.lib.b200sift_match_pairs_device(self.ctx.handle, len(pairs),
                                                        pr.ctypes.data_as(C.POINTER(C.c_int32)), int(desc_thresh),
                                                        float(ransac_thr), C.c_void_p(res.data_ptr()),
                                                        res.stride(0) * res.element_size()))
-        self._sync_streams(res.device, False)
 
 
 def sharded_panorama_shifts(images, backend, ransac_thr=3, desc_thresh=25000, dist=None, device='cpu'):
@@ -186,6 +185,13 @@ def sharded_panorama_shifts(images, backend, ransac_thr=3, desc_thresh=25000, di
     lo, hi = shard_range(n, rank, world)
     counts_local = np.asarray(backend.detect([images[i] for i in range(lo, hi)]), np.int64)
     _mark('detect')
+    with backend.stream_ctx(device):
+        return _exchange_and_match(images, backend, ransac_thr, desc_thresh, dist, device, rank, world, lo, hi, n,
+                                   counts_local)
+
+
+def _exchange_and_match(images, backend, ransac_thr, desc_thresh, dist, device, rank, world, lo, hi, n, counts_local):
+    import torch
 
     # ---- exchange: first image of every rank in ONE all-gather.  A keypoint travels as a 136-byte
     # row (128 B descriptor + 8 B xy); row 0 is a header (count, lo, block length), so no separate
