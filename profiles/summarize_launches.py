@@ -9,25 +9,26 @@ import sys
 
 def main(path, steps=None):
     lines = [l for l in open(path) if not l.startswith('==')]
+    rows = [r for r in csv.DictReader(lines) if r.get('Metric Name') == 'gpu__time_duration.sum']
+    names = [re.sub(r'^void ', '', re.sub(r'\(.*', '', r['Kernel Name'])) for r in rows]
+    # whole steps only: a step starts with the grey + upsample kernel; whatever follows the last
+    # complete step (e.g. the roofline launches bench.py makes after its timed loops) is dropped
+    starts = [i for i, k in enumerate(names) if k.endswith('gray_upsample_kernel')]
+    if len(starts) >= 2 and steps is None:
+        rows, names = rows[starts[0]:starts[-1]], names[starts[0]:starts[-1]]
+        steps = len(starts) - 1
     agg = collections.OrderedDict()
     tot = 0.0
     n = 0
-    first = None
-    for row in csv.DictReader(lines):
-        if row.get('Metric Name') != 'gpu__time_duration.sum':
-            continue
-        k = re.sub(r'\(.*', '', row['Kernel Name'])
-        k = re.sub(r'^void ', '', k)
+    for row, k in zip(rows, names):
         v = float(row['Metric Value'].replace(',', '')) * {'ns': 1e-3, 'us': 1.0, 'ms': 1e3}[row['Metric Unit']]
         a = agg.setdefault(k, [0, 0.0])
         a[0] += 1
         a[1] += v
         tot += v
         n += 1
-        if first is None:
-            first = k
     if steps is None:
-        steps = max(1, agg.get('b200::gray_upsample_kernel', [1])[0])
+        steps = 1
     print(f'{n} launches, {tot:.0f} us total, {steps} step(s) in the capture -> {tot / steps:.0f} us, '
           f'{n / steps:.0f} launches per step')
     print(f'{"us/step":>10} {"n/step":>7} {"us each":>9} {"share":>7}  kernel')
