@@ -15,9 +15,12 @@ pairs), sharded in contiguous blocks of 18 images per rank: per-GPU work is fixe
 scaling), block-boundary pairs need the neighbour rank's first image (one all-gather).  The
 strong-scaling time of the single 18-image set over N ranks is reported next to it
 (`strong_18_images`).
-`value`  : inputs already resident in HBM, device-timed (CUDA events on the launch stream).
+`value`  : inputs already resident in HBM; throughput over K steps with two steps in flight per GPU
+           (two library contexts per rank: the host round trips of one step overlap the kernels of
+           the other), device-timed with CUDA events around all K steps.
 `e2e`    : the same through the drop-in API with pinned HOST images in, host keypoints /
            descriptors / shifts out (H2D + D2H inside the timed region).
+`single_step`: one step at a time on one context (the latency of a single call), per-step events.
 One JSON line on stdout (rank 0).
 """
 import argparse
@@ -165,6 +168,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--depth', type=int, default=3, help='steps in flight per GPU (library contexts per rank)')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     rank = int(os.environ.get('RANK', '0'))
@@ -214,26 +218,77 @@ def main():
     # e2e outputs land in pinned host memory as well (allocated once, grown on demand)
     out_pin = {}
 
-    def pinned_out(total):
-        if out_pin.get('cap', 0) < total:
+    def pinned_out_for(slot, total):
+        st = out_pin.setdefault(slot, {})
+        if st.get('cap', 0) < total:
             cap = max(2 * total, 1 << 16)
             kp_bytes = torch.empty(cap * sift_impl.KP_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
             desc = torch.empty((cap, 128), dtype=torch.uint8).pin_memory()
-            out_pin.update(cap=cap, keep=(kp_bytes, desc),
-                           kps=kp_bytes.numpy().view(sift_impl.KP_DTYPE), desc=desc.numpy())
-        return out_pin['kps'], out_pin['desc']
+            st.update(cap=cap, keep=(kp_bytes, desc), kps=kp_bytes.numpy().view(sift_impl.KP_DTYPE), desc=desc.numpy())
+        return st['kps'], st['desc']
 
-    def step_e2e():
-        """host images in, host keypoints + descriptors + shifts out."""
-        if world == 1:
-            counts = sift_impl.detect_and_describe_batch(pinned_np, ctx=ctx, download=False)
-            shifts = iss.match_pairs([(i, i + 1) for i in range(n - 1)], 3, 25000, ctx)[0]
-            res = sift_impl.download_results(counts, ctx, out=pinned_out(int(np.sum(counts))))
-            return shifts, counts, res
-        shifts, counts = panorama.sharded_panorama_shifts(pinned_np, backend, dist=dist, device=dev)
-        res = sift_impl.download_results(backend.counts, ctx,        # this rank's block, to the host
-                                         out=pinned_out(int(np.sum(backend.counts))))
+    def e2e_job(_, c):
+        """host images in, host keypoints + descriptors + shifts out, on context `c`."""
+        counts = sift_impl.detect_and_describe_batch(pinned_np, ctx=c, download=False)
+        shifts = iss.match_pairs([(i, i + 1) for i in range(n - 1)], 3, 25000, c)[0]
+        res = sift_impl.download_results(counts, c, out=pinned_out_for(id(c), int(np.sum(counts))))
         return shifts, counts, res
+
+    DEPTH = args.depth      # image sets in flight per GPU (library contexts per rank)
+    extra_ctx = [_capi.Context(local) for _ in range(DEPTH - 1)]
+    all_ctx = [ctx] + extra_ctx
+
+    def launches_now():
+        return sum(c.launch_count() for c in all_ctx)
+
+    def timed_throughput(run, steps, warmup):
+        """`run(k)` processes k independent steps with DEPTH of them in flight.  Device time between two
+        events bracketing ALL steps (barrier + full device synchronisation on both sides) / steps, max
+        over ranks.  The per-step working set (0.47 GB of pyramid per 18 images) exceeds the 126 MB L2, so
+        consecutive steps cannot feed each other from cache; no flush is written between them."""
+        run(max(warmup, 2 * DEPTH))
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = launches_now()
+        e0.record()
+        t0 = time.perf_counter()
+        out = run(steps)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) / steps * 1e3
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps, wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), out, (launches_now() - l0) / steps
+
+    if world == 1:
+        # N = 1: pipeline.PanoramaPipeline -- DEPTH contexts, one host thread each; the uploads / downloads /
+        # host round trips of one set overlap the kernels of another
+        from vfx_image_stitching_b200.pipeline import PanoramaPipeline
+        pipe = PanoramaPipeline(contexts=all_ctx)
+
+        def run_resident(k):
+            return pipe.map(lambda _, c_: (iss.panorama_shifts(resident, ctx=c_), None), range(k))[-1]
+
+        def run_e2e(k):
+            return pipe.map(e2e_job, range(k))[-1]
+    else:
+        # N > 1: panorama.sharded_panorama_stream -- detect+describe of step k+1 (helper thread, other
+        # context) next to the exchange + matching of step k; all collectives from this thread, in order
+        backends = [backend] + [panorama.GpuBackend(c_) for c_ in extra_ctx]
+
+        def run_resident(k):
+            return panorama.sharded_panorama_stream([resident] * k, backends, dist=dist, device=dev)[-1]
+
+        def run_e2e(k):
+            def after(j, be, shifts, counts):            # this rank's block, to the (pinned) host
+                sift_impl.download_results(be.counts, be.ctx, out=pinned_out_for(id(be.ctx), int(np.sum(be.counts))))
+            return panorama.sharded_panorama_stream([pinned_np] * k, backends, dist=dist, device=dev, after=after)[-1]
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -262,8 +317,11 @@ def main():
         return float(t[0]), float(t[1]), out, (ctx.launch_count() - l0) / steps
 
     sampler = ClockSampler(local) if rank == 0 else None
-    ms_dev, wall_dev, out_dev, launches = timed(step_resident, args.steps, args.warmup)
-    ms_e2e, wall_e2e, out_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    ms_dev, wall_dev, out_dev, launches = timed_throughput(run_resident, args.steps, args.warmup)
+    ms_e2e, wall_e2e, out_e2e, _ = timed_throughput(run_e2e, args.steps, args.warmup)
+    # one step at a time on one context, per-step CUDA events, 256 MiB L2 flush before every step: the
+    # latency of a single call, reported next to the throughput numbers
+    ms_one, _, _, launches_one = timed(step_resident, max(5, args.steps // 2), 3)
     clocks = sampler.stop() if sampler else None
     strong = None
     if world > 1:   # the single 18-image set split over all ranks (strong scaling), for the record
@@ -330,11 +388,17 @@ def main():
                        'images': n, 'pairs': n - 1, 'keypoints': int(counts.sum()),
                        'sharding': f'contiguous blocks of {nb} images per rank over {world} rank(s); pair (i,i+1) on the '
                                    'owner of i; one all-gather of every block\'s first-image descriptors',
-                       'l2': 'per-step pyramid working set ~0.47 GB > 126 MB L2; plus a 256 MiB flush write before '
-                             'every timed step (outside the per-step CUDA events)'},
+                       'mode': f'throughput: {DEPTH} steps in flight per GPU ({DEPTH} library contexts per rank; N = 1: '
+                               'pipeline.PanoramaPipeline, N > 1: panorama.sharded_panorama_stream); device time over all '
+                               'steps / steps.  single_step = one step at a time, per-step CUDA events',
+                       'l2': 'inputs larger than L2: per-step pyramid working set ~0.47 GB per 18 images > 126 MB L2 '
+                             '(throughput legs, no flush); the single_step leg writes a 256 MiB flush before every step'},
             'e2e': {'value': mpix_step / (ms_e2e / 1e3), 'unit': UNIT, 'ms_per_step': ms_e2e,
-                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-            'gpu_launches': launches, 'wall_ms_per_step_incl_flush': wall_dev,
+                    'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                    'wall_ms_per_step': wall_e2e},
+            'gpu_launches': launches, 'wall_ms_per_step': wall_dev,
+            'single_step': {'ms_per_step': ms_one, 'value': mpix_step / (ms_one / 1e3), 'unit': UNIT,
+                            'gpu_launches': launches_one},
             'match_desc_pairs_per_s': desc_pairs / (ms_dev / 1e3), 'image_pairs_per_s': (n - 1) / (ms_dev / 1e3),
             'roofline': roof, 'cpu_baseline': cpu, 'clocks': clocks,
         }

@@ -83,6 +83,10 @@ def _worker(rank, world, port, q, min_rows=None):
     dist.init_process_group('gloo', init_method=f'tcp://127.0.0.1:{port}', rank=rank, world_size=world)
     try:
         shifts, counts = sharded_panorama_shifts(_images(), _oracle_backend(), dist=dist, device='cpu')
+        # throughput form: three jobs through two backends must give the same answer every time
+        stream = panorama.sharded_panorama_stream([_images()] * 3, [_oracle_backend(), _oracle_backend()], dist=dist,
+                                                  device='cpu')
+        assert all(s == shifts and c == counts for s, c in stream), rank
         q.put((rank, shifts, counts))
     finally:
         dist.destroy_process_group()

@@ -311,3 +311,25 @@ def test_cylindrical_projection_bit_exact(iss, oracle):
     img = natural_image(120, 160, 9, channels=3)
     for f in (704.9, 454.417, 90.0):
         assert np.array_equal(iss.cylindrical_projection(img, f), oracle.cylindrical_projection(img, f))
+
+
+def test_pipeline_equals_single_context(si, iss):
+    """Throughput mode (two contexts, two host threads on one GPU) returns exactly what the
+    one-context path returns, set by set."""
+    from vfx_image_stitching_b200.pipeline import PanoramaPipeline
+    sets = []
+    for k in range(5):
+        a = natural_image(160, 200, 20 + k, channels=3)
+        sets.append([a, np.roll(a, (2, -15 - k), axis=(0, 1)), np.roll(a, (4, -33), axis=(0, 1))])
+    pipe = PanoramaPipeline(depth=2)
+    try:
+        got = pipe.panorama_shifts(sets)
+        assert len(pipe.contexts) == 2
+    finally:
+        pipe.close()
+    for s, (shifts, counts, res) in zip(sets, got):
+        ref = si.detect_and_describe_batch(s)
+        assert [len(k) for k, _ in ref] == counts.tolist()
+        for (k0, d0), (k1, d1) in zip(ref, res):
+            assert np.array_equal(k0, k1) and np.array_equal(d0, d1)
+        assert shifts == iss.panorama_shifts(s)

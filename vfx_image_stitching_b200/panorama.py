@@ -261,3 +261,44 @@ def _exchange_and_match(images, backend, ransac_thr, desc_thresh, dist, device, 
     _mark('results')
     shifts = [(float(rows[i, 0]), float(rows[i, 1])) for i in range(n - 1)]
     return shifts, rows[:, 2].astype(np.int64).tolist()
+
+
+def sharded_panorama_stream(jobs, backends, ransac_thr=3, desc_thresh=25000, dist=None, device='cpu', after=None):
+    """Throughput form of sharded_panorama_shifts for a sequence of image lists (`jobs`).
+
+    Two stages per job: (1) detect+describe of the local block -- no communication, runs on a helper
+    thread; (2) exchange + matching + result all-gather -- every collective is issued from the calling
+    thread, in job order, so all ranks issue them in the same order.  Job k uses backends[k % len(backends)]
+    (one library context each): while stage 2 of job k runs, stage 1 of the next len(backends) - 1 jobs is
+    already on the GPU with the other contexts.  `after(k, backend, shifts, counts)` (optional) runs in the calling thread after job
+    k, e.g. to download its results.  Returns [(shifts, counts)] per job -- identical to calling
+    sharded_panorama_shifts job by job."""
+    from concurrent.futures import ThreadPoolExecutor
+    jobs = list(jobs)
+    n_be = len(backends)
+    if dist is None or not dist.is_initialized():
+        rank, world = 0, 1
+    else:
+        rank, world = dist.get_rank(), dist.get_world_size()
+
+    def stage1(k):
+        images = jobs[k]
+        lo, hi = shard_range(len(images), rank, world)
+        return lo, hi, np.asarray(backends[k % n_be].detect([images[i] for i in range(lo, hi)]), np.int64)
+
+    out = []
+    ahead = max(1, n_be - 1)   # stage-1 jobs in flight: job k+j uses backends[(k+j) % n_be], all distinct
+    with ThreadPoolExecutor(ahead) as pool:
+        futs = {k: pool.submit(stage1, k) for k in range(min(ahead, len(jobs)))}
+        for k in range(len(jobs)):
+            lo, hi, counts_local = futs.pop(k).result()
+            if k + ahead < len(jobs):
+                futs[k + ahead] = pool.submit(stage1, k + ahead)   # its context finished stage 2 of job k-1
+            be = backends[k % n_be]
+            with be.stream_ctx(device):
+                res = _exchange_and_match(jobs[k], be, ransac_thr, desc_thresh, dist, device, rank, world, lo, hi,
+                                          len(jobs[k]), counts_local)
+            if after is not None:
+                after(k, be, *res)
+            out.append(res)
+    return out
