@@ -407,6 +407,8 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        for be in backends:
+            be.close()                      # exchange buffers go before the communicator and the contexts
         dist.destroy_process_group()
 
 

@@ -41,7 +41,13 @@ def _worker(rank, world, port, q, min_rows):
         out = None
         for _ in range(2):   # second pass reuses the persistent exchange buffers
             out = panorama.sharded_panorama_shifts(_images(), backend, dist=dist, device=dev)
+        # throughput form: 4 jobs through 3 contexts (helper threads for detect, collectives in order)
+        backends = [backend, panorama.GpuBackend(_capi.Context(rank)), panorama.GpuBackend(_capi.Context(rank))]
+        stream = panorama.sharded_panorama_stream([_images()] * 4, backends, dist=dist, device=dev)
+        assert all(s == out[0] and c == out[1] for s, c in stream), rank
         q.put((rank, out[0], out[1]))
+        for be in backends:
+            be.close()
     finally:
         dist.destroy_process_group()
 

@@ -48,6 +48,13 @@ class BackendBase:
         import contextlib
         return contextlib.nullcontext()
 
+    def close(self):
+        """Release the persistent exchange buffers.  Call it before torch.distributed.destroy_process_group()
+        and before the library context goes away: the buffers were used by the collectives' streams and on
+        the context's stream, and freeing them after either is gone makes the caching allocator touch a
+        dead stream."""
+        self.__dict__.pop('_xchg', None)
+
     def pack_first(self, row, cap, tail, device):
         """Fill `row` ((cap+1, 136) uint8 on `device`) with the header + the first local image."""
         import torch
@@ -138,6 +145,12 @@ class GpuBackend(BackendBase):
     # copies and both NCCL collectives -- runs on the CONTEXT's stream (torch.distributed issues on the
     # current torch stream), so no events or cross-stream waits are needed; the only host
     # synchronisations are the header read-back inside unpack and the final result download.
+    def close(self):
+        import torch
+        BackendBase.close(self)
+        self._ext = None
+        torch.cuda.synchronize(self.ctx.device)
+
     def stream_ctx(self, device):
         import torch
         h = self.ctx.stream_handle()
