@@ -490,8 +490,10 @@ static int launch_blur_set(b200sift_ctx *c, const float *src, float *dst, int n_
                            size_t img_stride, int R, int tapset, float *dst2, int h2, int w2, int pitch2,
                            size_t img_stride2)
 {
+    // 16 B loads from src, 8 B (ring kernel) stores to dst: both row-aligned
     const bool strip_ok = (w >= 96) && (h >= 32) && (pitch % 4 == 0) &&
-                          ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && (img_stride % 4 == 0);
+                          ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (img_stride % 4 == 0);
     if (strip_ok) {
         if (use_ring_blur()) {
             switch (R) {
