@@ -48,6 +48,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--check', action='store_true')
     ap.add_argument('--out', default=None)
+    ap.add_argument('--depth', type=int, default=3, help='frames config: batches in flight (library contexts)')
     a = ap.parse_args()
     import torch
     from vfx_image_stitching_b200 import _capi, sift_impl
@@ -98,6 +99,24 @@ def main():
             if a.check:
                 kps, _ = sift_impl.download_results(counts, ctx)[0]
                 line['check_frame0'] = agreement(frames[0], kps)
+            if a.depth > 1:
+                # throughput mode: `steps` batches of these frames with `depth` of them in flight
+                # (pipeline.PanoramaPipeline: one library context + host thread per batch in flight)
+                from vfx_image_stitching_b200.pipeline import PanoramaPipeline
+                pipe = PanoramaPipeline(contexts=[ctx] + [_capi.Context(0) for _ in range(a.depth - 1)])
+                job = lambda _, c: sift_impl.detect_and_describe_batch(res_t, ctx=c, download=False)  # noqa: E731
+                pipe.map(job, range(2 * a.depth))
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                k = max(a.steps, 2 * a.depth)
+                pipe.map(job, range(k))
+                torch.cuda.synchronize()
+                e1.record()
+                torch.cuda.synchronize()
+                ms_t = e0.elapsed_time(e1) / k
+                line['throughput'] = {'depth': a.depth, 'batches': k, 'ms_per_batch': ms_t, 'mpix_per_s': mpix / (ms_t / 1e3)}
+                pipe.close()
         else:
             raise SystemExit(f'unknown config {name}')
         lines.append(line)
