@@ -26,6 +26,36 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, n), f'{n} declared in include/b200sift.h but not exported'
 
 
+def test_integration_doc_names_every_entry_point():
+    doc = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    missing = [n for n in _declared() if n not in doc]
+    assert not missing, missing
+
+
+def test_f4_signatures_and_host_logic(tmp_path):
+    """Row f4 mirrors: names / argument order of image_stitching_sift.py:12,139,156,208 and the pure host
+    logic (pano.txt parser, padding, drift correction) against the oracle's restatement -- no GPU involved."""
+    import inspect
+    from oracle import sift_oracle as so
+    from vfx_image_stitching_b200 import image_stitching_sift as iss
+    names = lambda f: [p.name for p in inspect.signature(f).parameters.values()]  # noqa: E731
+    assert names(iss.read_pano_data) == ['pano_file_path']
+    assert names(iss.pad_image) == ['img_bgr', 'move_x', 'move_y']
+    assert names(iss.blend_two_images)[:4] == ['shift_vec', 'ref_match', 'imgA', 'imgB']
+    assert names(iss.rectangle_crop)[:3] == ['img', 'black_threshold', 'extra_margin']
+    assert names(iss.cylindrical_projection)[:2] == ['img_bgr', 'focal_len']
+    fn = tmp_path / 'pano.txt'
+    fn.write_text('C:\\x\\a01.JPG\n384 512\n\n1 0 0\n0 1 0\n0 0 1\n\n704.5\nb02.png\nnot a number\n 12 \n703\n9.5\n',
+                  encoding='utf-8')
+    assert iss.read_pano_data(str(fn)) == so.read_pano_data(str(fn)) == (['C:\\x\\a01.JPG', 'b02.png'], [704.5, 12.0])
+    rng = np.random.default_rng(1)
+    img = rng.integers(0, 256, (7, 9, 3), dtype=np.uint8)
+    for mx, my in ((2.5, -1.5), (-3.4, 0.5), (0, 0), (1.5, 2.5)):
+        assert np.array_equal(iss.pad_image(img, mx, my), so.pad_image(img, mx, my))
+    shifts = [(-240.5, -4.25), (-251.0, 3.5), (-239.75, -6.0)]
+    assert iss.drift_corrected_shifts(shifts, 4) == so.drift_corrected_shifts(shifts, 4)
+
+
 def test_ctypes_prototypes_cover_header():
     from vfx_image_stitching_b200 import _capi
     assert sorted(_capi.PROTOTYPES) == _declared()
