@@ -2,9 +2,10 @@
 //
 // Replaces cv2.GaussianBlur(img,(0,0),sigma) on float32 (/root/reference/sift_impl.py:56,91).
 //
-// The scalar strip kernel (blur_strip.cuh) spends ~55 (R=5) .. ~95 (R=13) issue slots per pixel,
+// The scalar strip kernel (blur_strip.cuh) spends 54 (R=5) .. 86 (R=13) issue slots per pixel,
 // 60 % of them outside the FP32 pipe, and waits on its block barrier; this kernel does the same
-// 8 B/pixel job in ~18 .. ~40 slots:
+// 8 B/pixel job in 32 .. 55 slots (ncu: 14.0 M / 24.5 M warp instructions per 18 x 1024 x 768 layer
+// against 24.1 M / 38 M), without a block barrier in its loop:
 //   * every FADD / FMUL / FFMA works on an aligned PAIR of adjacent columns (add/mul/fma.f32x2 ->
 //     FADD2 / FMUL2 / FFMA2 on sm_100); the taps are uniform-register operands broadcast to both
 //     halves (`FFMA2 R, R, UR.F32, R`), so they cost no vector registers;
@@ -15,8 +16,14 @@
 //   * column pass: a thread owns a column pair; the row-filtered rows live in a shared-memory RING
 //     (2R + 16 rows), each ring row is read once per 8 output rows and scattered into 8
 //     accumulator pairs (16 registers instead of a 2R-deep register window, no window moves);
-//   * a warp fills (cp.async, 16 B) exactly the two input rows it row-filters, so the only
-//     block-wide dependency is the ring: ONE barrier per batch of 8 rows, 128 threads per CTA;
+//   * 256 threads in two roles.  Warps 0-3 (producers) fill -- 16 B cp.async, each warp exactly the
+//     two input rows it row-filters, so the input stages need only __syncwarp -- and run the row
+//     pass; warps 4-7 (consumers) run the column pass and the stores.  The ring is handed over
+//     slot by slot with one mbarrier pair (full / empty) per slot; there is no __syncthreads in the
+//     loop, and a producer may run one batch ahead of the consumers;
+//   * image borders: chunks are fetched wherever they lie inside the row allocation, and the columns
+//     left of 0 / right of w-1 are patched shared -> shared from their REFLECT_101 sources once the
+//     batch has landed, so no lane ever waits on a scalar global load;
 //   * shared rows are linear with an ODD number of 16 B chunks per row; even lanes work on the
 //     warp's first row and odd lanes on its second, so the eight lanes of a quarter warp (32 B apart
 //     within a row) hit eight distinct bank groups without any address swizzle;
