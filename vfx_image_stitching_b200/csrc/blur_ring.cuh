@@ -2,10 +2,11 @@
 //
 // Replaces cv2.GaussianBlur(img,(0,0),sigma) on float32 (/root/reference/sift_impl.py:56,91).
 //
-// The scalar strip kernel (blur_strip.cuh) spends 54 (R=5) .. 86 (R=13) issue slots per pixel,
-// 60 % of them outside the FP32 pipe, and waits on its block barrier; this kernel does the same
-// 8 B/pixel job in 32 .. 55 slots (ncu: 14.0 M / 24.5 M warp instructions per 18 x 1024 x 768 layer
-// against 24.1 M / 38 M), without a block barrier in its loop:
+// The scalar strip kernel (blur_strip.cuh) spends 54 issue slots per pixel at R = 5 (more for the
+// wider kernels), 60 % of them outside the FP32 pipe, and waits on its block barrier; this kernel
+// does the same 8 B/pixel job in 32 (R = 5) .. 55 (R = 13) slots (ncu, warp instructions per
+// 18 x 1024 x 768 layer at R = 5: 14.0 M against 24.1 M; R = 13: 24.5 M), without a block barrier in
+// its loop:
 //   * every FADD / FMUL / FFMA works on an aligned PAIR of adjacent columns (add/mul/fma.f32x2 ->
 //     FADD2 / FMUL2 / FFMA2 on sm_100); the taps are uniform-register operands broadcast to both
 //     halves (`FFMA2 R, R, UR.F32, R`), so they cost no vector registers;
