@@ -116,3 +116,11 @@ def test_no_cpu_fallback_without_gpu():
     from vfx_image_stitching_b200._capi import B200SiftError
     with pytest.raises(B200SiftError):
         sift_impl.compute_keypoints_and_descriptors(np.zeros((32, 32), np.uint8))
+
+
+@pytest.mark.skipif(_has_gpu(), reason='checks the behaviour WITHOUT a GPU')
+def test_pipeline_needs_a_gpu():
+    from vfx_image_stitching_b200._capi import B200SiftError
+    from vfx_image_stitching_b200.pipeline import PanoramaPipeline
+    with pytest.raises(B200SiftError):
+        PanoramaPipeline(depth=2)
