@@ -38,6 +38,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = 'sift_detect_describe_match_mpix_per_s'
 UNIT = 'Mpix/s'
+# the same string in both arms (the driver compares the two config.workload fields)
+WORKLOAD = 'parrington 18 x 384x512 detect+describe + 17 adjacent-pair match + vote (BASELINE.json configs[1])'
 
 
 def load_workload():
@@ -150,7 +152,7 @@ def reference_arm(args, rank):
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': data,
-        'config': {'workload': 'parrington 18 x 384x512 detect+describe + 17 adjacent-pair match + vote',
+        'config': {'workload': WORKLOAD,
                    'note': 'the reference is pure Python (no compiled sources, oracle/_ref does not exist); this arm '
                            'times the C restatement oracle/sift_oracle.c on all host threads'},
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
@@ -187,9 +189,10 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        os.environ.pop('NCCL_DEBUG', None)     # its version banner goes to stdout; keep that to the one JSON line
-        if os.environ.get('B200SIFT_NCCL_DEBUG'):
-            os.environ['NCCL_DEBUG'] = os.environ['B200SIFT_NCCL_DEBUG']
+        # NCCL_DEBUG stays as the caller set it: the driver reads the communicator's init lines.  Its
+        # banner would share stdout with the JSON line, so it is sent to stderr unless the caller chose a file.
+        if os.environ.get('NCCL_DEBUG') and not os.environ.get('NCCL_DEBUG_FILE'):
+            os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'
         dist.init_process_group('nccl', device_id=dev)
     ctx = _capi.default_context(local)
     stream = torch.cuda.Stream(dev)
@@ -382,9 +385,8 @@ def main():
             'metric': METRIC, 'value': mpix_step / (ms_dev / 1e3), 'unit': UNIT, 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': data,
-            'config': {'workload': 'parrington 18 x 384x512 detect+describe + 17 adjacent-pair match + vote '
-                                   '(BASELINE.json configs[1])' +
-                                   (f'; {world} such sets chained in pano order ({n} images, {n - 1} pairs)' if world > 1 else ''),
+            'config': {'workload': WORKLOAD,
+                       'chain': f'{world} such set(s) chained in pano order ({n} images, {n - 1} pairs): per-GPU work is fixed',
                        'images': n, 'pairs': n - 1, 'keypoints': int(counts.sum()),
                        'sharding': f'contiguous blocks of {nb} images per rank over {world} rank(s); pair (i,i+1) on the '
                                    'owner of i; one all-gather of every block\'s first-image descriptors',

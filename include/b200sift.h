@@ -70,8 +70,8 @@ typedef struct {
     int32_t ori_bins;           /* 36   */
     double peak_ratio;          /* 0.8  */
     double scale_factor;        /* 1.5  */
-    int32_t window_width;       /* 4   (fixed by the kernels) */
-    int32_t desc_bins;          /* 8   (fixed by the kernels) */
+    int32_t window_width;       /* 4   (any value with window_width^2 * desc_bins <= 1024) */
+    int32_t desc_bins;          /* 8   (the 4 x 4 x 8 default has its own specialised kernel) */
     double scale_multiplier;    /* 3    */
     double descriptor_max_value;/* 0.2  */
 } b200sift_params;
@@ -149,6 +149,21 @@ B200SIFT_API int b200sift_device_results(b200sift_ctx *ctx, int image, const uin
 B200SIFT_API int b200sift_match(b200sift_ctx *ctx, const uint8_t *A, int nA, const uint8_t *B, int nB,
                    int on_device, int32_t *best_idx, int32_t *best_d2, int32_t *second_d2);
 
+/* Nearest / second-nearest ratio test (sift_visualizeUI.py:247-257: knnMatch(k = 2), keep m when
+ * m.distance < 0.7 * n.distance) with EXACT neighbours (the reference asks approximate FLANN
+ * KD-trees) and exact integers: row i of A is accepted iff it has two neighbours and
+ * ratio_den^2 * best_d2 < ratio_num^2 * second_d2 (ratio = ratio_num / ratio_den, 7 / 10 in the
+ * reference).  ia / ib (capacity nA) receive the accepted A rows in order and their nearest B rows,
+ * *n_good their number; best_d2 / second_d2 (nA each, may be NULL) the squared distances of every row. */
+B200SIFT_API int b200sift_ratio_match(b200sift_ctx *ctx, const uint8_t *A, int nA, const uint8_t *B, int nB,
+                                      int on_device, int ratio_num, int ratio_den, int32_t *ia, int32_t *ib,
+                                      int32_t *best_d2, int32_t *second_d2, int32_t *n_good);
+
+/* Grid shape of the last tensor-core matcher launch of this context: B tiles (256 rows) per CTA
+ * and the number of B chunks (diagnostic; the parity tests use it to prove that the shared-memory
+ * ring and the TMEM double buffer wrapped). */
+B200SIFT_API int b200sift_match_grid(b200sift_ctx *ctx, int32_t *tiles_per_chunk, int32_t *n_chunks);
+
 /* compute_shift_sift's match list (image_stitching_sift.py:63-79) between two
  * images of the last detect_describe: accepted iff best_d2 < desc_thresh.
  * ia/ib (capacity = keypoints of imgA) receive the A / B keypoint indices in
@@ -203,9 +218,9 @@ B200SIFT_API int b200sift_match_pairs_device(b200sift_ctx *ctx, int n_pairs, con
                                              double dist_sq_thresh, void *dst, size_t dst_stride);
 
 /* ransac() translation vote (image_stitching_sift.py:86-111) on the device:
- * matches n x 4 float (xA,yA,xB,yB); returns the winning index in *best
- * (first maximum; -1 when n == 0) and its (dx,dy) in move[2]. */
-B200SIFT_API int b200sift_ransac(b200sift_ctx *ctx, const float *matches, int n, double dist_sq_thresh,
+ * matches n x 4 float64 (xA,yA,xB,yB) -- the reference votes on Python floats; any n; returns the
+ * winning index in *best (first maximum; -1 when n == 0) and its (dx,dy) in move[2]. */
+B200SIFT_API int b200sift_ransac(b200sift_ctx *ctx, const double *matches, int n, double dist_sq_thresh,
                     double *move, int32_t *best);
 
 /* ---------------------------------------------------------------------
@@ -236,19 +251,44 @@ B200SIFT_API int b200sift_dog_pyramid(b200sift_ctx *ctx, const float *const *lay
                          int n_layers, float *const *out_dogs);
 
 /* find_scale_space_extrema (sift_impl.py:117-140) on a caller-supplied
- * Gaussian pyramid (DoG = float32 difference of adjacent layers, as :109).
- * Keypoints come back in the reference's scan order, in base-image
- * coordinates, not de-duplicated.  *n receives the count (<= capacity). */
+ * Gaussian pyramid.  dog_layers = the caller's dog_images ([o*(n_layers-1)+l],
+ * extrema and the quadratic fit read them, as :124-129 do), or NULL: the DoG
+ * is then the float32 difference of adjacent Gaussian layers (:109), never
+ * materialised.  Keypoints come back in the reference's scan order, in
+ * base-image coordinates, not de-duplicated.  *n receives the count
+ * (<= capacity). */
 B200SIFT_API int b200sift_find_extrema(b200sift_ctx *ctx, const b200sift_params *params,
-                          const float *const *layers, int h, int w, int n_octaves, int n_layers,
-                          b200sift_keypoint *kps, int capacity, int32_t *n);
+                          const float *const *layers, const float *const *dog_layers, int h, int w,
+                          int n_octaves, int n_layers, b200sift_keypoint *kps, int capacity, int32_t *n);
+
+/* localize_extremum_via_quadratic_fit (sift_impl.py:169-211, with the gradient / Hessian of
+ * :217-240) for n caller-supplied candidates, results in input order.  cand = n x (octave, layer,
+ * y, x) int32 (the format of b200sift_extrema_candidates).  layers: is_dog != 0 -> DoG layers
+ * (n_layers = num_intervals + 2; what the reference passes as dog_images[octave]), else Gaussian
+ * layers (n_layers = num_intervals + 3; the cube is formed from their float32 differences).
+ * octave_base < 0: layers hold a whole pyramid of n_octaves octaves (h x w = octave 0); otherwise
+ * they hold ONLY octave `octave_base` (n_octaves = 1, h x w = that octave) and every candidate must
+ * name it.  kps[i] receives pt / size / response / octave (angle = -1 like cv2.KeyPoint()),
+ * final_layer[i] the layer the reference returns next to the keypoint, or -1 where it returns None. */
+B200SIFT_API int b200sift_localize(b200sift_ctx *ctx, const b200sift_params *params, const float *const *layers,
+                                   int is_dog, int h, int w, int n_octaves, int n_layers, int octave_base,
+                                   const int32_t *cand, int n, b200sift_keypoint *kps, int32_t *final_layer);
+
+/* compute_keypoints_with_orientations (sift_impl.py:246-293) for n keypoints on ONE Gaussian image
+ * (h x w float32, the reference's gauss_img argument; `octave` is its octave argument).  Keypoint i
+ * yields counts[i] oriented keypoints at out[i * ori_bins ...], ascending in histogram bin like the
+ * list the reference returns; out holds n * params->ori_bins records. */
+B200SIFT_API int b200sift_orientations(b200sift_ctx *ctx, const b200sift_params *params,
+                                       const b200sift_keypoint *kps, int n, int octave, const float *gauss_img,
+                                       int h, int w, b200sift_keypoint *out, int32_t *counts);
 
 /* remove_duplicate_keypoints (sift_impl.py:314-327): sort by compare_keypoints
  * (:299-311) and drop repeats; in place, *n_out receives the new count. */
 B200SIFT_API int b200sift_remove_duplicates(b200sift_ctx *ctx, b200sift_keypoint *kps, int n, int32_t *n_out);
 
 /* generate_descriptors (sift_impl.py:361-526) for keypoints already converted
- * to input-image size, on a caller-supplied Gaussian pyramid. */
+ * to input-image size, on a caller-supplied Gaussian pyramid.  desc_f32 is
+ * (n, window_width^2 * desc_bins) row-major, 128 columns with the defaults. */
 B200SIFT_API int b200sift_descriptors(b200sift_ctx *ctx, const b200sift_params *params,
                          const b200sift_keypoint *kps, int n, const float *const *layers, int h,
                          int w, int n_octaves, int n_layers, float *desc_f32);

@@ -87,6 +87,14 @@ def test_reference_signatures_are_preserved():
     assert sig(sift_impl.generate_descriptors) == [
         ('keypoints', None), ('gaussian_images', None), ('window_width', 4), ('num_bins', 8),
         ('scale_multiplier', 3), ('descriptor_max_value', 0.2)]
+    assert sig(sift_impl.localize_extremum_via_quadratic_fit) == [
+        ('x', None), ('y', None), ('layer', None), ('octave', None), ('num_intervals', None), ('dog_octave', None),
+        ('sigma', None), ('contrast_threshold', None), ('border', None), ('eigen_ratio', 10), ('max_iter', 5)]
+    assert sig(sift_impl.compute_keypoints_with_orientations) == [
+        ('keypoint', None), ('octave', None), ('gauss_img', None), ('radius_factor', 3), ('num_bins', 36),
+        ('peak_ratio', 0.8), ('scale_factor', 1.5)]
+    assert sig(sift_impl.is_pixel_an_extremum) == [
+        ('prev_patch', None), ('curr_patch', None), ('next_patch', None), ('threshold', None)]
     assert sig(image_stitching_sift.compute_shift_sift)[:4] == [
         ('imgA', None), ('imgB', None), ('ransac_thr', 3), ('desc_thresh', 25000)]
     assert sig(image_stitching_sift.ransac)[:2] == [('matches', None), ('dist_sq_thresh', 3)]
@@ -96,6 +104,46 @@ def test_reference_signatures_are_preserved():
                  'compare_keypoints', 'remove_duplicate_keypoints', 'convert_keypoints_to_input_image_size',
                  'unpack_octave'):
         assert callable(getattr(sift_impl, name))
+
+
+def test_every_reference_function_is_mirrored():
+    """All 17 top-level functions of the reference's sift_impl.py exist in the drop-in with the
+    same parameter names in the same order; checked against the list recorded from the reference source."""
+    import inspect
+    from vfx_image_stitching_b200 import sift_impl
+    ref = {  # name -> positional parameter names, /root/reference/sift_impl.py (def lines 15 ... 361)
+        'compute_keypoints_and_descriptors': ['image', 'sigma', 'num_intervals', 'assumed_blur', 'image_border_width'],
+        'generate_base_image': ['image', 'sigma', 'assumed_blur'],
+        'compute_number_of_octaves': ['image_shape'],
+        'generate_gaussian_kernels': ['sigma', 'num_intervals'],
+        'generate_gaussian_images': ['image', 'num_octaves', 'gaussian_kernels'],
+        'generate_DoG_images': ['gaussian_images'],
+        'find_scale_space_extrema': ['gaussian_images', 'dog_images', 'num_intervals', 'sigma', 'border',
+                                     'contrast_threshold'],
+        'is_pixel_an_extremum': ['prev_patch', 'curr_patch', 'next_patch', 'threshold'],
+        'localize_extremum_via_quadratic_fit': ['x', 'y', 'layer', 'octave', 'num_intervals', 'dog_octave', 'sigma',
+                                                'contrast_threshold', 'border', 'eigen_ratio', 'max_iter'],
+        'compute_gradient_at_center_pixel': ['cube'],
+        'compute_hessian_at_center_pixel': ['cube'],
+        'compute_keypoints_with_orientations': ['keypoint', 'octave', 'gauss_img', 'radius_factor', 'num_bins',
+                                                'peak_ratio', 'scale_factor'],
+        'compare_keypoints': ['kp1', 'kp2'],
+        'remove_duplicate_keypoints': ['keypoints'],
+        'convert_keypoints_to_input_image_size': ['keypoints'],
+        'unpack_octave': ['keypoint'],
+        'generate_descriptors': ['keypoints', 'gaussian_images', 'window_width', 'num_bins', 'scale_multiplier',
+                                 'descriptor_max_value'],
+    }
+    assert len(ref) == 17
+    for name, params in ref.items():
+        assert [p.name for p in inspect.signature(getattr(sift_impl, name)).parameters.values()] == params, name
+
+
+def test_desc_thresh_is_the_reference_comparison():
+    """`dist < desc_thresh` on integer distances (image_stitching_sift.py:74) for non-integer thresholds."""
+    from vfx_image_stitching_b200.image_stitching_sift import _int_thresh
+    assert _int_thresh(25000) == 25000 and _int_thresh(25000.5) == 25001 and _int_thresh(24999.0001) == 25000
+    assert _int_thresh(-3.5) == -3 and _int_thresh(1e12) == 2 ** 31 - 1
 
 
 def test_host_side_parameter_arithmetic_matches_oracle(oracle):

@@ -119,3 +119,33 @@ def test_sharded_equals_single_process(world, min_rows):
         assert p.exitcode == 0
     for rank, shifts, counts in got:
         assert shifts == ref_shifts and counts == ref_counts, rank
+
+
+@pytest.mark.parametrize('n_backends', [1, 2, 3])
+def test_stream_distinct_jobs_keep_their_own_results(n_backends):
+    """sharded_panorama_stream with DISTINCT jobs: job k must get job k's results for any number of
+    backends -- with a single backend stage 1 of job k+1 must not start before stage 2 of job k has
+    read that backend's results (round-1 advisor finding)."""
+    import time
+    from vfx_image_stitching_b200.panorama import BackendBase, sharded_panorama_stream
+
+    class Tagged(BackendBase):
+        def __init__(self):
+            self.tag = None
+
+        def detect(self, images):
+            self.tag = images[0]
+            return np.array([images[0]] * len(images), np.int32)
+
+        def match_pairs(self, pairs, ransac_thr, desc_thresh):
+            time.sleep(0.01)                       # stage 2 reads the backend's state late
+            return [(float(self.tag), float(p[1])) for p in pairs]
+
+    jobs = [[k + 1] * 3 for k in range(6)]
+    seen = []
+    out = sharded_panorama_stream(jobs, [Tagged() for _ in range(n_backends)],
+                                  after=lambda k, be, shifts, counts: seen.append((k, be.tag)))
+    assert [k for k, _ in seen] == list(range(6))
+    for k, (shifts, counts) in enumerate(out):
+        assert shifts == [(float(k + 1), 1.0), (float(k + 1), 2.0)], (k, shifts)
+        assert counts == [k + 1] * 3

@@ -69,7 +69,11 @@ PROTOTYPES = {
     'b200sift_base_image': (_i, [_vp, _vp, _i, _i, _d, _d, _vp]),
     'b200sift_gaussian_pyramid': (_i, [_vp, _vp, _i, _i, _i, C.POINTER(C.c_double), _i, _pp]),
     'b200sift_dog_pyramid': (_i, [_vp, _pp, _i, _i, _i, _i, _pp]),
-    'b200sift_find_extrema': (_i, [_vp, C.POINTER(Params), _pp, _i, _i, _i, _i, _vp, _i, _ip]),
+    'b200sift_find_extrema': (_i, [_vp, C.POINTER(Params), _pp, _pp, _i, _i, _i, _i, _vp, _i, _ip]),
+    'b200sift_localize': (_i, [_vp, C.POINTER(Params), _pp, _i, _i, _i, _i, _i, _i, _vp, _i, _vp, _vp]),
+    'b200sift_orientations': (_i, [_vp, C.POINTER(Params), _vp, _i, _i, _vp, _i, _i, _vp, _vp]),
+    'b200sift_ratio_match': (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _ip]),
+    'b200sift_match_grid': (_i, [_vp, _ip, _ip]),
     'b200sift_extrema_candidates': (_i, [_vp, C.POINTER(Params), _pp, _i, _i, _i, _i, _vp, _i, _ip]),
     'b200sift_remove_duplicates': (_i, [_vp, _vp, _i, _ip]),
     'b200sift_descriptors': (_i, [_vp, C.POINTER(Params), _vp, _i, _pp, _i, _i, _i, _i, _vp]),

@@ -3,6 +3,7 @@
 // match.cu.  No arithmetic of the path happens on the host.
 #include <math.h>
 #include <algorithm>
+#include <mutex>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -126,11 +127,11 @@ static void gaussian_sigmas(double sigma, int num_intervals, double *out)
 
 // Upload a caller-supplied Gaussian pyramid (dense host layers, octave-major,
 // n_layers per octave) into the context pyramid (n_img = 1).
-static int upload_pyramid(b200sift_ctx *c, const float *const *layers, int h, int w, int n_oct, int n_layers)
+static int upload_pyramid_into(b200sift_ctx *c, Pyramid &p, const float *const *layers, int h, int w, int n_oct,
+                               int n_layers)
 {
     B200_ARG(layers != nullptr);
-    B200_CHECK(pyramid_layout(c, 1, h, w, n_oct, n_layers));
-    const Pyramid &p = c->pyr;
+    B200_CHECK(pyramid_layout_into(p, 1, h, w, n_oct, n_layers));
     for (int o = 0; o < n_oct; ++o)
         for (int l = 0; l < n_layers; ++l) {
             const float *src = layers[o * n_layers + l];
@@ -138,6 +139,29 @@ static int upload_pyramid(b200sift_ctx *c, const float *const *layers, int h, in
             B200_CUDA(cudaMemcpy2DAsync(p.layer(o, l), (size_t)p.pitch[o] * 4, src, (size_t)p.w[o] * 4,
                                         (size_t)p.w[o] * 4, p.h[o], cudaMemcpyHostToDevice, c->stream));
         }
+    return 0;
+}
+
+static int upload_pyramid(b200sift_ctx *c, const float *const *layers, int h, int w, int n_oct, int n_layers)
+{
+    c->oct_events_valid = false;
+    return upload_pyramid_into(c, c->pyr, layers, h, w, n_oct, n_layers);
+}
+
+// Kernel function attributes (dynamic shared memory opt-in, carve-out) are per device and the
+// library serves several devices / several contexts per device from concurrent host threads: they
+// are set exactly once per device, here, and never from a launch path.
+static std::mutex g_init_lock;
+static bool g_device_ready[64] = {};
+
+static int init_device_once(int device)
+{
+    std::lock_guard<std::mutex> guard(g_init_lock);
+    if (device < 64 && g_device_ready[device]) return 0;
+    B200_CHECK(pyramid_init_device());
+    B200_CHECK(detect_init_device());
+    B200_CHECK(match_init_device());
+    if (device < 64) g_device_ready[device] = true;
     return 0;
 }
 
@@ -202,6 +226,7 @@ int b200sift_create(int device, b200sift_ctx **out)
         set_error("device %d is sm_%d%d; libb200sift is built for sm_100a only", device, prop.major, prop.minor);
         return B200SIFT_ECUDA;
     }
+    B200_CHECK(init_device_once(device));
     b200sift_ctx *c = new b200sift_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
@@ -227,7 +252,8 @@ void b200sift_destroy(b200sift_ctx *c)
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->pyr.base, c->d_up, c->d_in, c->d_dog, c->d_cand, c->d_loc, c->d_raw, c->d_raw_desc,
                     c->d_sort_idx, c->d_keep, c->d_pos, c->d_cub_tmp, c->d_kps, c->d_desc, c->d_counters,
-                    c->d_mA, c->d_mB, c->d_mout, c->d_nrmB, c->d_misc, c->d_pair, c->d_tc, c->d_tcsrc, c->d_seg, c->d_ptrs};
+                    c->d_mA, c->d_mB, c->d_mout, c->d_misc, c->d_pair, c->d_tc, c->d_tcsrc, c->d_seg, c->d_ptrs,
+                    c->d_taps, c->dog_pyr.base};
     if (c->h_ptrs) cudaFreeHost(c->h_ptrs);
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -388,6 +414,7 @@ int b200sift_get_keypoints(b200sift_ctx *c, int image, b200sift_keypoint *kps, f
     B200_ARG(image >= 0 && image < c->n_img_last);
     const int off = c->img_off[image], n = c->img_off[image + 1] - off;
     if (n == 0) return 0;
+    B200_CUDA(cudaSetDevice(c->device));
     if (kps)
         B200_CUDA(cudaMemcpyAsync(kps, c->d_kps + off, sizeof(b200sift_keypoint) * n, cudaMemcpyDeviceToHost,
                                   c->stream));
@@ -424,6 +451,7 @@ int b200sift_get_all_keypoints(b200sift_ctx *c, b200sift_keypoint *kps, uint8_t 
         set_error("get_all_keypoints: capacity %lld < %d keypoints", (long long)capacity, n);
         return B200SIFT_EARG;
     }
+    B200_CUDA(cudaSetDevice(c->device));
     if (kps)
         B200_CUDA(cudaMemcpyAsync(kps, c->d_kps, sizeof(b200sift_keypoint) * (size_t)n, cudaMemcpyDeviceToHost,
                                   c->stream));
@@ -507,6 +535,7 @@ int b200sift_match_images(b200sift_ctx *c, int imgA, int imgB, int desc_thresh, 
     const int offA = c->img_off[imgA], nA = c->img_off[imgA + 1] - offA;
     const int offB = c->img_off[imgB], nB = c->img_off[imgB + 1] - offB;
     if (nA == 0) return 0;
+    B200_CUDA(cudaSetDevice(c->device));
     // scratch: idx, d1, d2, ia, ib (int32 x nA each), xyxy (float x 4nA), count
     size_t cap = c->misc_cap;
     B200_CHECK(ensure((uint8_t **)&c->d_misc, &cap, (size_t)(nA * 9 + 4) * sizeof(int32_t)));
@@ -586,6 +615,7 @@ int b200sift_get_pair_matches(b200sift_ctx *c, int p, int32_t *ia, int32_t *ib, 
     }
     const int n = c->pair_counts[p];
     if (n == 0) return 0;
+    B200_CUDA(cudaSetDevice(c->device));
     const size_t mo = (size_t)p * c->pair_rows_max;
     if (ia) B200_CUDA(cudaMemcpyAsync(ia, c->d_pair_ia + mo, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
     if (ib) B200_CUDA(cudaMemcpyAsync(ib, c->d_pair_ib + mo, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
@@ -788,7 +818,7 @@ int b200sift_match_pairs_device(b200sift_ctx *c, int n_pairs, const int32_t *pai
     return 0;
 }
 
-int b200sift_ransac(b200sift_ctx *c, const float *matches, int n, double thr, double *move, int32_t *best)
+int b200sift_ransac(b200sift_ctx *c, const double *matches, int n, double thr, double *move, int32_t *best)
 {
     B200_ARG(c && move && best && n >= 0);
     move[0] = move[1] = 0;
@@ -797,10 +827,10 @@ int b200sift_ransac(b200sift_ctx *c, const float *matches, int n, double thr, do
     B200_ARG(matches != nullptr);
     B200_CUDA(cudaSetDevice(c->device));
     size_t cap = c->mA_cap;
-    B200_CHECK(ensure(&c->d_mA, &cap, (size_t)n * 16));
+    B200_CHECK(ensure(&c->d_mA, &cap, (size_t)n * 32));
     c->mA_cap = cap;
-    B200_CUDA(cudaMemcpyAsync(c->d_mA, matches, (size_t)n * 16, cudaMemcpyHostToDevice, c->stream));
-    return launch_ransac(c, (const float *)c->d_mA, n, thr, move, best);
+    B200_CUDA(cudaMemcpyAsync(c->d_mA, matches, (size_t)n * 32, cudaMemcpyHostToDevice, c->stream));
+    return launch_ransac(c, (const double *)c->d_mA, n, thr, move, best);
 }
 
 // ------------------------------------------------------------------ stage API
@@ -858,7 +888,7 @@ int b200sift_base_image(b200sift_ctx *c, const float *image, int h, int w, doubl
 int b200sift_gaussian_pyramid(b200sift_ctx *c, const float *base, int h, int w, int n_oct, const double *sigmas,
                               int n_layers, float *const *out_layers)
 {
-    B200_ARG(c && base && sigmas && out_layers && n_oct >= 1);
+    B200_ARG(c && base && sigmas && out_layers && n_oct >= 1 && n_layers >= 4);
     B200_CUDA(cudaSetDevice(c->device));
     c->have_results = false;
     B200_CHECK(pyramid_layout(c, 1, h, w, n_oct, n_layers));
@@ -902,8 +932,9 @@ int b200sift_dog_pyramid(b200sift_ctx *c, const float *const *layers, int h, int
     return 0;
 }
 
-int b200sift_find_extrema(b200sift_ctx *c, const b200sift_params *params, const float *const *layers, int h, int w,
-                          int n_oct, int n_layers, b200sift_keypoint *kps, int capacity, int32_t *n)
+int b200sift_find_extrema(b200sift_ctx *c, const b200sift_params *params, const float *const *layers,
+                          const float *const *dog_layers, int h, int w, int n_oct, int n_layers,
+                          b200sift_keypoint *kps, int capacity, int32_t *n)
 {
     B200_ARG(c && n && capacity >= 0);
     b200sift_params P;
@@ -912,7 +943,8 @@ int b200sift_find_extrema(b200sift_ctx *c, const b200sift_params *params, const 
     B200_CUDA(cudaSetDevice(c->device));
     c->have_results = false;
     B200_CHECK(upload_pyramid(c, layers, h, w, n_oct, n_layers));
-    B200_CHECK(run_detect(c, P, 1));
+    if (dog_layers) B200_CHECK(upload_pyramid_into(c, c->dog_pyr, dog_layers, h, w, n_oct, n_layers - 1));
+    B200_CHECK(run_detect(c, P, dog_layers != nullptr));
     fill_stats(c);
     const int n_raw = c->h_counters[CNT_RAW];
     B200_CHECK(run_sort_gather(c, n_raw, 1, /*scan_order=*/1, /*dedupe=*/0, /*convert=*/0, /*with_desc=*/0));
@@ -940,7 +972,7 @@ int b200sift_extrema_candidates(b200sift_ctx *c, const b200sift_params *params, 
     B200_CUDA(cudaSetDevice(c->device));
     c->have_results = false;
     B200_CHECK(upload_pyramid(c, layers, h, w, n_oct, n_layers));
-    B200_CHECK(run_detect(c, P, 1));
+    B200_CHECK(run_detect(c, P, 0));
     const int nc = c->h_counters[CNT_CAND];
     *n = nc;
     if (nc > capacity) {
@@ -949,7 +981,8 @@ int b200sift_extrema_candidates(b200sift_ctx *c, const b200sift_params *params, 
     }
     if (nc == 0) return 0;
     std::vector<Candidate> hc(nc);
-    B200_CUDA(cudaMemcpy(hc.data(), c->d_cand, sizeof(Candidate) * nc, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpyAsync(hc.data(), c->d_cand, sizeof(Candidate) * nc, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
     // device order is arbitrary (atomic compaction); hand back the reference's scan order
     std::vector<uint64_t> key(nc);
     for (int i = 0; i < nc; ++i)
@@ -986,7 +1019,8 @@ int b200sift_remove_duplicates(b200sift_ctx *c, b200sift_keypoint *kps, int n, i
     B200_CUDA(cudaMemcpyAsync(c->d_raw, raw.data(), sizeof(RawKeypoint) * n, cudaMemcpyHostToDevice, c->stream));
     B200_CHECK(run_sort_gather(c, n, 1, 0, 1, 0, 0));
     const int m = c->img_off[1];
-    B200_CUDA(cudaMemcpy(kps, c->d_kps, sizeof(b200sift_keypoint) * m, cudaMemcpyDeviceToHost));
+    B200_CUDA(cudaMemcpyAsync(kps, c->d_kps, sizeof(b200sift_keypoint) * m, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
     *n_out = m;
     return 0;
 }
@@ -1008,13 +1042,110 @@ int b200sift_descriptors(b200sift_ctx *c, const b200sift_params *params, const b
         raw[i].response = kps[i].response; raw[i].octave_packed = kps[i].octave;
         raw[i].img = 0; raw[i].pad = 0; raw[i].order = (uint64_t)i;
     }
+    B200_ARG(P.window_width >= 1 && P.desc_bins >= 1 && P.window_width * P.window_width * P.desc_bins <= 1024);
+    const size_t dlen = (size_t)P.window_width * P.window_width * P.desc_bins;
     B200_CHECK(ensure_sparse_for(c, 1, n));
+    uint8_t *d_out = c->d_raw_desc;               // [raw_cap][128]
+    if (dlen > 128) {
+        size_t cap = c->misc_cap;
+        B200_CHECK(ensure((uint8_t **)&c->d_misc, &cap, (size_t)n * dlen));
+        c->misc_cap = cap;
+        d_out = (uint8_t *)c->d_misc;
+    }
     B200_CUDA(cudaMemcpyAsync(c->d_raw, raw.data(), sizeof(RawKeypoint) * n, cudaMemcpyHostToDevice, c->stream));
-    B200_CHECK(run_describe(c, P, c->d_raw, n, /*converted=*/1, c->d_raw_desc));
-    std::vector<uint8_t> u8((size_t)n * 128);
-    B200_CUDA(cudaMemcpyAsync(u8.data(), c->d_raw_desc, u8.size(), cudaMemcpyDeviceToHost, c->stream));
+    B200_CHECK(run_describe(c, P, c->d_raw, n, /*converted=*/1, d_out));
+    std::vector<uint8_t> u8((size_t)n * dlen);
+    B200_CUDA(cudaMemcpyAsync(u8.data(), d_out, u8.size(), cudaMemcpyDeviceToHost, c->stream));
     B200_CUDA(cudaStreamSynchronize(c->stream));
     for (size_t i = 0; i < u8.size(); ++i) desc_f32[i] = (float)u8[i];
+    return 0;
+}
+
+int b200sift_localize(b200sift_ctx *c, const b200sift_params *params, const float *const *layers, int is_dog, int h,
+                      int w, int n_oct, int n_layers, int octave_base, const int32_t *cand, int n,
+                      b200sift_keypoint *kps, int32_t *final_layer)
+{
+    B200_ARG(c && n >= 0);
+    if (n == 0) return 0;
+    B200_ARG(layers && cand && kps && final_layer && n_oct >= 1 && (octave_base < 0 || n_oct == 1));
+    b200sift_params P;
+    if (params) P = *params; else b200sift_default_params(&P);
+    B200_ARG(n_layers == P.num_intervals + (is_dog ? 2 : 3));
+    B200_CUDA(cudaSetDevice(c->device));
+    c->have_results = false;
+    if (is_dog) B200_CHECK(upload_pyramid_into(c, c->dog_pyr, layers, h, w, n_oct, n_layers));
+    else B200_CHECK(upload_pyramid(c, layers, h, w, n_oct, n_layers));
+    if (octave_base >= 0)
+        for (int i = 0; i < n; ++i) B200_ARG(cand[4 * i] == octave_base);
+    return run_localize_direct(c, P, is_dog, octave_base >= 0, cand, n, kps, final_layer);
+}
+
+int b200sift_orientations(b200sift_ctx *c, const b200sift_params *params, const b200sift_keypoint *kps, int n,
+                          int octave, const float *gauss_img, int h, int w, b200sift_keypoint *out, int32_t *counts)
+{
+    B200_ARG(c && n >= 0);
+    if (n == 0) return 0;
+    B200_ARG(kps && gauss_img && out && counts && h >= 3 && w >= 3);
+    b200sift_params P;
+    if (params) P = *params; else b200sift_default_params(&P);
+    B200_CUDA(cudaSetDevice(c->device));
+    c->have_results = false;
+    const float *one[1] = {gauss_img};
+    B200_CHECK(upload_pyramid(c, one, h, w, 1, 1));
+    return run_orient_direct(c, P, kps, n, octave, out, counts);
+}
+
+int b200sift_ratio_match(b200sift_ctx *c, const uint8_t *A, int nA, const uint8_t *B, int nB, int on_device,
+                         int ratio_num, int ratio_den, int32_t *ia, int32_t *ib, int32_t *best_d2,
+                         int32_t *second_d2, int32_t *n_good)
+{
+    B200_ARG(c && n_good && nA >= 0 && nB >= 0 && ratio_num > 0 && ratio_den > 0 && ratio_num < 32768 &&
+             ratio_den < 32768);
+    *n_good = 0;
+    if (nA == 0) return 0;
+    B200_ARG(A != nullptr && (nB == 0 || B != nullptr));
+    B200_CUDA(cudaSetDevice(c->device));
+    const uint8_t *dA = A, *dB = B;
+    if (!on_device) {
+        size_t cap = c->mA_cap;
+        B200_CHECK(ensure(&c->d_mA, &cap, (size_t)nA * 128));
+        c->mA_cap = cap;
+        cap = c->mB_cap;
+        B200_CHECK(ensure(&c->d_mB, &cap, (size_t)(nB > 0 ? nB : 1) * 128));
+        c->mB_cap = cap;
+        B200_CUDA(cudaMemcpyAsync(c->d_mA, A, (size_t)nA * 128, cudaMemcpyHostToDevice, c->stream));
+        if (nB) B200_CUDA(cudaMemcpyAsync(c->d_mB, B, (size_t)nB * 128, cudaMemcpyHostToDevice, c->stream));
+        dA = c->d_mA;
+        dB = c->d_mB;
+    }
+    size_t cap = c->misc_cap;
+    B200_CHECK(ensure((uint8_t **)&c->d_misc, &cap, (size_t)(nA * 5 + 4) * sizeof(int32_t)));
+    c->misc_cap = cap;
+    int32_t *d_idx = (int32_t *)c->d_misc, *d_b1 = d_idx + nA, *d_b2 = d_b1 + nA, *d_ia = d_b2 + nA, *d_ib = d_ia + nA,
+            *d_cnt = d_ib + nA;
+    Timer tm(c);
+    B200_CHECK(run_match(c, dA, nA, dB, nB, d_idx, d_b1, d_b2));
+    B200_CHECK(run_ratio_accept(c, d_idx, d_b1, d_b2, nA, ratio_num, ratio_den, d_ia, d_ib, d_cnt));
+    tm.stop();
+    int32_t n = 0;
+    B200_CUDA(cudaMemcpyAsync(&n, d_cnt, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
+    if (best_d2) B200_CUDA(cudaMemcpyAsync(best_d2, d_b1, sizeof(int32_t) * nA, cudaMemcpyDeviceToHost, c->stream));
+    if (second_d2) B200_CUDA(cudaMemcpyAsync(second_d2, d_b2, sizeof(int32_t) * nA, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    if (n > 0) {
+        if (ia) B200_CUDA(cudaMemcpyAsync(ia, d_ia, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+        if (ib) B200_CUDA(cudaMemcpyAsync(ib, d_ib, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+        B200_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    *n_good = n;
+    return 0;
+}
+
+int b200sift_match_grid(b200sift_ctx *c, int32_t *tiles_per_chunk, int32_t *n_chunks)
+{
+    B200_ARG(c != nullptr);
+    if (tiles_per_chunk) *tiles_per_chunk = c->last_tiles_per_chunk;
+    if (n_chunks) *n_chunks = c->last_n_chunks;
     return 0;
 }
 

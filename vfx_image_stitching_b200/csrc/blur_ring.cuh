@@ -2,11 +2,11 @@
 //
 // Replaces cv2.GaussianBlur(img,(0,0),sigma) on float32 (/root/reference/sift_impl.py:56,91).
 //
-// The scalar strip kernel (blur_strip.cuh) spends 54 issue slots per pixel at R = 5 (more for the
-// wider kernels), 60 % of them outside the FP32 pipe, and waits on its block barrier; this kernel
-// does the same 8 B/pixel job in 32 (R = 5) .. 55 (R = 13) slots (ncu, warp instructions per
-// 18 x 1024 x 768 layer at R = 5: 14.0 M against 24.1 M; R = 13: 24.5 M), without a block barrier in
-// its loop:
+// A scalar strip kernel (round 1, now tools/experiments/blur_strip.cuh) spent 54 issue slots per
+// pixel at R = 5 (more for the wider kernels), 60 % of them outside the FP32 pipe, and waited on its
+// block barrier; this kernel does the same 8 B/pixel job in 32 (R = 5) .. 55 (R = 13) slots (ncu,
+// warp instructions per 18 x 1024 x 768 layer at R = 5: 14.0 M against 24.1 M; R = 13: 24.5 M),
+// without a block barrier in its loop:
 //   * every FADD / FMUL / FFMA works on an aligned PAIR of adjacent columns (add/mul/fma.f32x2 ->
 //     FADD2 / FMUL2 / FFMA2 on sm_100); the taps are uniform-register operands broadcast to both
 //     halves (`FFMA2 R, R, UR.F32, R`), so they cost no vector registers;
@@ -41,6 +41,18 @@
 // the reference's own IPP-on and IPP-off blurs differ by 7.6e-5).
 // dst2 (optional) receives the [::2, ::2] decimation that seeds the next octave (sift_impl.py:95-96).
 #pragma once
+
+template <int R>
+struct BlurTaps {
+    float t[R + 1];  // centre .. R
+};
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
 
 constexpr int kRingW = 256;      // strip width (columns)
 constexpr int kRingBR = 8;       // rows per batch

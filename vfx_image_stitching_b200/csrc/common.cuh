@@ -69,6 +69,14 @@ struct PyrView {
     }
 };
 
+// Gaussian tap sets of one context: host mirror + sigma cache of b200sift_ctx::d_taps (pyramid.cu).
+struct TapCache {
+    double sigma[16] = {};
+    int radius[16] = {};
+    bool valid[16] = {};
+    float taps[16][kMaxBlurRadius + 1] = {};
+};
+
 // 3x3x3 extremum that passed is_pixel_an_extremum.
 struct Candidate {
     uint32_t img_o_l;  // img << 16 | octave << 8 | layer
@@ -132,10 +140,13 @@ struct b200sift_ctx {
     long long launches = 0;
 
     b200::Pyramid pyr;
+    b200::TapCache taps;            // Gaussian tap sets of this context (host mirror)
+    float *d_taps = nullptr;        // [16][kMaxBlurRadius + 1] in global memory
     float *d_up = nullptr;  size_t up_cap = 0;     // upsampled (pre-blur) base, [img][2h][pitch0]
     uint8_t *d_in = nullptr; size_t in_cap = 0;    // uploaded input images
     void **d_ptrs = nullptr, **h_ptrs = nullptr; size_t ptrs_cap = 0;  // pointer table of device-resident inputs
     float *d_dog = nullptr; size_t dog_cap = 0;    // materialised DoG (stage API only)
+    b200::Pyramid dog_pyr;                         // caller-supplied DoG layers (stage API only)
 
     // sparse stage
     b200::Candidate *d_cand = nullptr; int cand_cap = 0;
@@ -159,7 +170,6 @@ struct b200sift_ctx {
     // matcher scratch
     uint8_t *d_mA = nullptr, *d_mB = nullptr; size_t mA_cap = 0, mB_cap = 0;
     int32_t *d_mout = nullptr; size_t mout_cap = 0;
-    int32_t *d_nrmB = nullptr; size_t nrmB_cap = 0;
     void *d_misc = nullptr; size_t misc_cap = 0;
     uint8_t *d_pair = nullptr; size_t pair_cap = 0;   // batched pair matching scratch
     uint8_t *d_tc = nullptr; size_t tc_cap = 0;       // tensor-core matcher: packed descriptors + norms
@@ -167,6 +177,7 @@ struct b200sift_ctx {
     uint8_t *d_tcsrc = nullptr; size_t tcsrc_cap = 0; // generic match(): A and B side by side
     b200::PairResult *d_pair_res = nullptr; int32_t *d_pair_ia = nullptr, *d_pair_ib = nullptr;
     float *d_pair_xy = nullptr; int pair_rows_max = 0, pair_n = 0;
+    int last_tiles_per_chunk = 0, last_n_chunks = 0;   // grid shape of the last tensor-core matcher launch
     std::vector<int> pair_counts;
     std::vector<b200::PairDesc> h_pair_desc;
 };
@@ -190,8 +201,13 @@ int ensure(T **p, size_t *cap, size_t need)
     return 0;
 }
 
+// one-time per-device kernel attributes (b200sift_create, under the init lock)
+int pyramid_init_device();
+int detect_init_device();
+int match_init_device();
 // pyramid.cu
-int pyramid_layout(b200sift_ctx *c, int n_img, int h0, int w0, int n_oct, int n_layers);
+int pyramid_layout(b200sift_ctx *c, int n_img, int h0, int w0, int n_oct, int n_layers);   // c->pyr
+int pyramid_layout_into(Pyramid &p, int n_img, int h0, int w0, int n_oct, int n_layers);
 int launch_gray_upsample(b200sift_ctx *c, const void *d_in, size_t img_stride_bytes, const void *const *d_ptrs,
                          size_t row_stride, int n_img, int h, int w, int channels, int dtype, float *d_out,
                          int out_pitch);
@@ -204,19 +220,26 @@ int launch_dog(b200sift_ctx *c, const float *a, const float *b, float *out, size
 // detect.cu
 PyrView make_view(const b200sift_ctx *c);
 DetectParams make_detect_params(const b200sift_params &p);
-int run_detect(b200sift_ctx *c, const b200sift_params &p, int want_scan_order);
+int run_detect(b200sift_ctx *c, const b200sift_params &p, int use_dog);
+PyrView make_view(const Pyramid &p);
+int run_localize_direct(b200sift_ctx *c, const b200sift_params &p, int use_dog, int single_octave,
+                        const int32_t *h_cand, int n, b200sift_keypoint *h_kps, int32_t *h_final_layer);
+int run_orient_direct(b200sift_ctx *c, const b200sift_params &p, const b200sift_keypoint *h_kps, int n, int octave,
+                      b200sift_keypoint *h_out, int32_t *h_counts);
 int run_describe(b200sift_ctx *c, const b200sift_params &p, const RawKeypoint *d_raw, int n, int converted,
                  uint8_t *d_out);
 int run_sort_gather(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int dedupe, int convert, int with_desc);
 int run_sort_async(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int dedupe);   // on the side stream
 int run_gather(b200sift_ctx *c, int n_raw, int n_img, int dedupe, int convert, int with_desc);
 int ensure_sparse_for(b200sift_ctx *c, int n_img, int n_raw);
-int launch_ransac(b200sift_ctx *c, const float *d_matches, int n, double thr, double *move, int32_t *best);
+int launch_ransac(b200sift_ctx *c, const double *d_matches, int n, double thr, double *move, int32_t *best);
 int launch_cyl(b200sift_ctx *c, const uint8_t *d_src, int h, int w, int ch, double f, uint8_t *d_dst);
 // match.cu
 int run_match(b200sift_ctx *c, const uint8_t *dA, int nA, const uint8_t *dB, int nB, int32_t *d_best_idx,
               int32_t *d_best_d2, int32_t *d_second_d2);
 int run_match_pairs(b200sift_ctx *c, int n_pairs, const int *h_pairs, int thresh, double vote_thr);
+int run_ratio_accept(b200sift_ctx *c, const int32_t *d_idx, const int32_t *d_d1, const int32_t *d_d2, int nA, int num,
+                     int den, int32_t *d_ia, int32_t *d_ib, int32_t *d_count);
 int bench_match_tc(b200sift_ctx *c, int nA, int nB, int top2, int iters, float *ms_kernel);
 int run_accept(b200sift_ctx *c, const int32_t *d_idx, const int32_t *d_d2, int nA, int thresh,
                const b200sift_keypoint *kA, const b200sift_keypoint *kB, int32_t *d_ia, int32_t *d_ib,

@@ -378,3 +378,120 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
         __syncwarp();
     }
 }
+
+// ---------------------------------------------------------------------------
+// generate_descriptors for any (window_width, num_bins) (sift_impl.py:361-362 keyword arguments;
+// the kernel above is the 4 x 4 x 8 default).  One warp per keypoint, every lane walks its share of
+// the clipped window and adds its trilinear shares to a lane-private histogram of the INNER
+// window_width^2 x num_bins cells ([bin][lane] in dynamic shared memory, <= 1024 bins); the 32
+// histograms are summed in a fixed order.  Same dtypes as the kernel above.
+// ---------------------------------------------------------------------------
+constexpr int kDescGenericMaxBins = 1024;
+
+__global__ void __launch_bounds__(32)
+describe_generic_kernel(PyrView v, DetectParams dp, int d, int nb, const RawKeypoint *__restrict__ raw, int n,
+                        int converted, uint8_t *__restrict__ desc_out)
+{
+    extern __shared__ __align__(16) float ghist[];   // [d*d*nb][32]
+    const int lane = threadIdx.x;
+    const int dlen = d * d * nb;
+    for (int ki = blockIdx.x; ki < n; ki += gridDim.x) {
+        const RawKeypoint K = raw[ki];
+        const float kx = converted ? K.x : K.x * 0.5f, ky = converted ? K.y : K.y * 0.5f;
+        const float ksize = converted ? K.size : K.size * 0.5f;
+        const int koct = converted ? K.octave_packed : ((K.octave_packed & ~255) | ((K.octave_packed - 1) & 255));
+        int octv = koct & 255;
+        const int lyr = (koct >> 8) & 255;
+        if (octv >= 128) octv |= -128;
+        const float scl = octv >= 0 ? 1.f / (float)(1 << octv) : (float)(1 << -octv);
+        const int po = octv + 1;
+        const bool ok = (po >= 0 && po < v.n_oct && lyr < v.n_layers);
+        const int rows = ok ? v.h[po] : 1, cols = ok ? v.w[po] : 1, pitch = ok ? v.pitch[po] : 1;
+        const float *img = ok ? v.layer(po, lyr, K.img) : nullptr;
+        const int ptx = (int)rint((double)scl * (double)kx);
+        const int pty = (int)rint((double)scl * (double)ky);
+        const double angle = 360. - (double)K.angle;
+        const double rad = angle * (3.14159265358979323846 / 180.0);
+        const double cos_a = cos(rad), sin_a = sin(rad);
+        const float hist_width = (float)dp.scale_multiplier_half * scl * ksize;
+        int half_w = (int)rint((double)hist_width * 1.4142135623730951 * (d + 1) * 0.5);
+        const int diag = (int)sqrt((double)((long long)rows * rows + (long long)cols * cols));
+        half_w = min(half_w, diag);
+        const double inv_hw = 1.0 / (double)hist_width;
+        const float anglef = (float)angle;
+        const float bins_per_deg = (float)(nb / 360.);
+        const float wmul = (float)(-0.5 / ((0.5 * d) * (0.5 * d)));
+        const double shift = 0.5 * d - 0.5;
+        for (int b = 0; b < dlen; ++b) ghist[b * 32 + lane] = 0.f;
+        const int rlo = max(pty - half_w, 1), rhi = min(pty + half_w, rows - 2);
+        const int clo = max(ptx - half_w, 1), chi = min(ptx + half_w, cols - 2);
+        const int nx = chi - clo + 1, ny = rhi - rlo + 1;
+        const int total = (ok && nx > 0 && ny > 0) ? nx * ny : 0;
+        for (int idx = lane; idx < total; idx += 32) {
+            const int yy = idx / nx, xx = idx - yy * nx;
+            const int ys = rlo + yy - pty, xs = clo + xx - ptx;
+            const double r_rot = xs * sin_a + ys * cos_a;
+            const double c_rot = xs * cos_a - ys * sin_a;
+            const double qr = r_rot * inv_hw, qc = c_rot * inv_hw;
+            const double r_bin = qr + shift, c_bin = qc + shift;
+            if (!(r_bin > -1.0 && r_bin < (double)d && c_bin > -1.0 && c_bin < (double)d)) continue;
+            const float *p = img + (size_t)(pty + ys) * pitch + (ptx + xs);
+            const float gx = __ldg(p + 1) - __ldg(p - 1);
+            const float gy = __ldg(p - pitch) - __ldg(p + pitch);
+            const float mag = sqrtf(gx * gx + gy * gy);
+            const float orient = mod360f(atan2f(gy, gx) * B200_RAD2DEGF);
+            const float fqr = (float)qr, fqc = (float)qc;
+            const float wm = expf(wmul * (fqr * fqr + fqc * fqc)) * mag;
+            float ob = (orient - anglef) * bins_per_deg;          // np.mod(ob, nb) in float32
+            ob = fmodf(ob, (float)nb);
+            if (ob != 0.f) { if (ob < 0.f) ob += (float)nb; } else ob = 0.f;
+            const int r0 = __double2int_rd(r_bin), c0 = __double2int_rd(c_bin);
+            int o0 = (int)floorf(ob);                             // in [0, nb]: ob + nb can round up to nb
+            if (o0 >= nb) o0 -= nb;                               // o0 % num_bins (:461); `of` is then nb (:465)
+            const int o1 = o0 + 1 < nb ? o0 + 1 : 0;
+            const float rf = (float)(r_bin - (double)r0), cf = (float)(c_bin - (double)c0);
+            const float of = ob - (float)o0;
+            const float c1 = wm * rf, c0w = wm - c1;
+            const float mv[4] = {c0w * (1.f - cf), c0w * cf, c1 * (1.f - cf), c1 * cf};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int rb = r0 + (k >> 1), cb = c0 + (k & 1);
+                if ((unsigned)rb < (unsigned)d && (unsigned)cb < (unsigned)d) {   // inner cells only (:509)
+                    float *cell = ghist + ((rb * d + cb) * nb) * 32 + lane;
+                    cell[o0 * 32] += mv[k] * (1.f - of);
+                    cell[o1 * 32] += mv[k] * of;
+                }
+            }
+        }
+        __syncwarp();
+        // fixed-order sum of the 32 private histograms -> element e in ghist[e*32] (lane e % 32 owns it)
+        double ss = 0.0;
+        for (int e = lane; e < dlen; e += 32) {
+            float s = 0.f;
+            for (int l = 0; l < 32; ++l) s += ghist[e * 32 + ((l + lane) & 31)];
+            __syncwarp();
+            ghist[e * 32] = s;
+            ss += (double)(s * s);
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, sft);
+        const float thr = sqrtf((float)ss) * dp.descriptor_max_value_f;
+        double ss2 = 0.0;
+        for (int e = lane; e < dlen; e += 32) {
+            float s = ghist[e * 32];
+            if (s > thr) s = thr;
+            ghist[e * 32] = s;
+            ss2 += (double)(s * s);
+        }
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) ss2 += __shfl_xor_sync(0xffffffffu, ss2, sft);
+        float norm_v = sqrtf((float)ss2);
+        if (norm_v < 1e-7f) norm_v = 1e-7f;
+        for (int e = lane; e < dlen; e += 32) {
+            float t = rintf(512.f * (ghist[e * 32] / norm_v));
+            t = fminf(fmaxf(t, 0.f), 255.f);
+            desc_out[(size_t)ki * dlen + e] = (uint8_t)t;
+        }
+        __syncwarp();
+    }
+}

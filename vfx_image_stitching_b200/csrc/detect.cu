@@ -22,9 +22,8 @@ namespace b200 {
 // counters layout
 enum { CNT_CAND = 0, CNT_LOC = 1, CNT_RAW = 2, CNT_OUT = 3, CNT_WORK_DESC = 4, CNT_WORK_ORI = 5, CNT_HDR = 8, CNT_PER_IMG = 4 };
 
-PyrView make_view(const b200sift_ctx *c)
+PyrView make_view(const Pyramid &p)
 {
-    const Pyramid &p = c->pyr;
     PyrView v;
     v.n_img = p.n_img;
     v.n_oct = p.n_oct;
@@ -37,6 +36,8 @@ PyrView make_view(const b200sift_ctx *c)
     }
     return v;
 }
+
+PyrView make_view(const b200sift_ctx *c) { return make_view(c->pyr); }
 
 DetectParams make_detect_params(const b200sift_params &p)
 {
@@ -65,8 +66,11 @@ DetectParams make_detect_params(const b200sift_params &p)
 // layers); each thread tests its pixels in the num_intervals middle layers;
 // hits are compacted with a warp ballot and one atomic per warp.
 // ---------------------------------------------------------------------------
+// kDog: `v` already holds DoG layers (find_scale_space_extrema with a caller-supplied dog_images,
+// sift_impl.py:117-118) and they are loaded as they are.
 constexpr int kExTW = 32, kExTH = 16;
 
+template <bool kDog>
 __global__ void __launch_bounds__(256)
 extrema_kernel(PyrView v, int o, int border, int num_intervals, float thresh, Candidate *__restrict__ cand,
                int cand_cap, int32_t *__restrict__ counters)
@@ -75,7 +79,7 @@ extrema_kernel(PyrView v, int o, int border, int num_intervals, float thresh, Ca
     constexpr int SW = kExTW + 2, SH = kExTH + 2, SN = SW * SH;
     const int img = blockIdx.z;
     const int h = v.h[o], w = v.w[o], pitch = v.pitch[o];
-    const int n_dog = v.n_layers - 1;
+    const int n_dog = kDog ? v.n_layers : v.n_layers - 1;
     const int x0 = border + blockIdx.x * kExTW, y0 = border + blockIdx.y * kExTH;
     const size_t lstride = (size_t)v.n_img * h * pitch;  // layer stride
     const float *g0 = v.layer(o, 0, img);
@@ -85,10 +89,14 @@ extrema_kernel(PyrView v, int o, int border, int num_intervals, float thresh, Ca
         const float *p = g0 + (size_t)y * pitch + x;
         float prev = *p;
         for (int l = 0; l < n_dog; ++l) {
-            p += lstride;
-            const float cur = *p;
-            dog_s[l * SN + i] = __fsub_rn(cur, prev);
-            prev = cur;
+            if (kDog) {
+                dog_s[l * SN + i] = p[(size_t)l * lstride];
+            } else {
+                p += lstride;
+                const float cur = *p;
+                dog_s[l * SN + i] = __fsub_rn(cur, prev);
+                prev = cur;
+            }
         }
     }
     __syncthreads();
@@ -345,20 +353,35 @@ __device__ __forceinline__ void sym3_solve(const double H[3][3], const double g[
     x[2] = (C * g[0] + E * g[1] + F * g[2]) * inv;
 }
 
+// kDog: `v` holds DoG layers (a caller-supplied dog_images / dog_octave) instead of Gaussian layers.
+// direct_n >= 0 is the per-call form of the stage API (localize_extremum_via_quadratic_fit on a
+// caller's candidates): exactly direct_n candidates, result i written to loc[i] (img_o_l =
+// 0xFFFFFFFF when the reference returns None), no counters; direct_single_octave: `v` holds only
+// the candidate's octave (as octave 0) while the candidate's own octave number scales the result.
+template <bool kDog>
 __global__ void __launch_bounds__(128)
 refine_kernel(PyrView v, DetectParams dp, const Candidate *__restrict__ cand, int cand_cap,
-              Localized *__restrict__ loc, int loc_cap, int32_t *__restrict__ counters)
+              Localized *__restrict__ loc, int loc_cap, int32_t *__restrict__ counters, int direct_n,
+              int direct_single_octave)
 {
-    const int n = min(counters[CNT_CAND], cand_cap);
+    const bool direct = direct_n >= 0;
+    const int n = direct ? direct_n : min(counters[CNT_CAND], cand_cap);
     for (int ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += gridDim.x * blockDim.x) {
         const Candidate cd = cand[ci];
         const int img = cd.img_o_l >> 16, o = (cd.img_o_l >> 8) & 255;
         int layer = cd.img_o_l & 255;
         int y = cd.yx >> 16, x = cd.yx & 0xffff;
         const uint64_t order = ((((uint64_t)o << 4) | (uint64_t)layer) << 30) | ((uint64_t)y << 15) | (uint64_t)x;
-        const int h = v.h[o], w = v.w[o], pitch = v.pitch[o];
+        const int ov = direct_single_octave ? 0 : o;
+        const int h = v.h[ov], w = v.w[ov], pitch = v.pitch[ov];
         const size_t lstride = (size_t)v.n_img * h * pitch;
-        const float *g0 = v.layer(o, 0, img);
+        const float *g0 = v.layer(ov, 0, img);
+        if (direct) {
+            Localized none;
+            none.x = none.y = none.size = none.response = 0.f;
+            none.octave_packed = 0; none.img_o_l = 0xFFFFFFFFu; none.order = order;
+            loc[ci] = none;
+        }
         float cube[3][3][3], grad[3], hess[3][3], upd[3];
         bool alive = true;
         for (int it = 0; it < dp.max_iter; ++it) {
@@ -369,10 +392,16 @@ refine_kernel(PyrView v, DetectParams dp, const Candidate *__restrict__ cand, in
 #pragma unroll
                 for (int i = 0; i < 3; ++i) {
                     const float *q = p + j * pitch + i;
-                    const float a0 = q[0], a1 = q[lstride], a2 = q[2 * lstride], a3 = q[3 * lstride];
-                    cube[0][j][i] = __fdiv_rn(__fsub_rn(a1, a0), 255.f);
-                    cube[1][j][i] = __fdiv_rn(__fsub_rn(a2, a1), 255.f);
-                    cube[2][j][i] = __fdiv_rn(__fsub_rn(a3, a2), 255.f);
+                    if (kDog) {
+                        cube[0][j][i] = __fdiv_rn(q[0], 255.f);
+                        cube[1][j][i] = __fdiv_rn(q[lstride], 255.f);
+                        cube[2][j][i] = __fdiv_rn(q[2 * lstride], 255.f);
+                    } else {
+                        const float a0 = q[0], a1 = q[lstride], a2 = q[2 * lstride], a3 = q[3 * lstride];
+                        cube[0][j][i] = __fdiv_rn(__fsub_rn(a1, a0), 255.f);
+                        cube[1][j][i] = __fdiv_rn(__fsub_rn(a2, a1), 255.f);
+                        cube[2][j][i] = __fdiv_rn(__fsub_rn(a3, a2), 255.f);
+                    }
                 }
             grad[0] = 0.5f * (cube[1][1][2] - cube[1][1][0]);
             grad[1] = 0.5f * (cube[1][2][1] - cube[1][0][1]);
@@ -438,6 +467,10 @@ refine_kernel(PyrView v, DetectParams dp, const Candidate *__restrict__ cand, in
         L.response = fabsf(val);
         L.img_o_l = ((uint32_t)img << 16) | ((uint32_t)o << 8) | (uint32_t)layer;
         L.order = order;
+        if (direct) {
+            loc[ci] = L;
+            continue;
+        }
         const int slot = atomicAdd(&counters[CNT_LOC], 1);
         atomicAdd(&counters[CNT_HDR + img * CNT_PER_IMG + 1], 1);
         if (slot < loc_cap) loc[slot] = L;
@@ -464,14 +497,19 @@ constexpr int kOriWarps = 4;
 constexpr int kOriMaxBins = 36;
 __global__ void __launch_bounds__(kOriWarps * 32)
 orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int loc_cap,
-              RawKeypoint *__restrict__ raw, int raw_cap, int32_t *__restrict__ counters)
+              RawKeypoint *__restrict__ raw, int raw_cap, int32_t *__restrict__ counters, int direct_n,
+              int32_t *__restrict__ direct_counts)
 {
+    // direct_n >= 0: the per-call form of the stage API (compute_keypoints_with_orientations on a
+    // caller's keypoints and ONE Gaussian image, held by `v` as octave 0 / layer 0): the peaks of
+    // keypoint i go to raw[i * ori_bins ...] in ascending bin order, their number to direct_counts[i].
+    const bool direct = direct_n >= 0;
     __shared__ double hist_s[kOriWarps][kOriMaxBins][32];
     __shared__ double raw_s[kOriWarps][kOriMaxBins];
     __shared__ double smooth_s[kOriWarps][kOriMaxBins];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nb = dp.ori_bins;  // <= 36
-    const int n = min(counters[CNT_LOC], loc_cap);
+    const int n = direct ? direct_n : min(counters[CNT_LOC], loc_cap);
     const int warps_total = gridDim.x * kOriWarps;
     double(*hist)[32] = hist_s[wib];
     (void)warps_total;
@@ -482,8 +520,9 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
         if (li >= n) break;
         const Localized L = loc[li];
         const int img = L.img_o_l >> 16, o = (L.img_o_l >> 8) & 255, layer = L.img_o_l & 255;
-        const int h = v.h[o], w = v.w[o], pitch = v.pitch[o];
-        const float *gimg = v.layer(o, layer, img);
+        const int ov = direct ? 0 : o;
+        const int h = v.h[ov], w = v.w[ov], pitch = v.pitch[ov];
+        const float *gimg = v.layer(ov, direct ? 0 : layer, img);
         const float scale = (float)(dp.scale_factor * (double)L.size) / (float)(1 << (o + 1));
         const int radius = (int)fminf(rintf(dp.radius_factor_f * scale), 1048576.f);
         const float weight_fac = -0.5f / (scale * scale);
@@ -588,11 +627,15 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
             const unsigned m = __ballot_sync(0xffffffffu, peak);
             if (m) {
                 int base = 0;
-                if (lane == __ffs(m) - 1) {
-                    base = atomicAdd(&counters[CNT_RAW], __popc(m));
-                    atomicAdd(&counters[CNT_HDR + img * CNT_PER_IMG + 2], __popc(m));
+                if (direct) {
+                    base = li * nb + emitted;
+                } else {
+                    if (lane == __ffs(m) - 1) {
+                        base = atomicAdd(&counters[CNT_RAW], __popc(m));
+                        atomicAdd(&counters[CNT_HDR + img * CNT_PER_IMG + 2], __popc(m));
+                    }
+                    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
                 }
-                base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
                 if (peak) {
                     const int slot = base + __popc(m & ((1u << lane) - 1u));
                     double t = (double)b + 0.5 * (sl - sr) / (sl - 2 * sc + sr);
@@ -613,7 +656,7 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
                 emitted += __popc(m);
             }
         }
-        (void)emitted;
+        if (direct && lane == 0) direct_counts[li] = emitted;
         __syncwarp();
     }
 }
@@ -713,6 +756,7 @@ gather_kernel(const RawKeypoint *__restrict__ raw, const uint8_t *__restrict__ r
 // order in which the atomics filled the segment.  Larger images take the CUB merge sort below.
 // ---------------------------------------------------------------------------
 constexpr int kSortMaxPerImage = 4096;
+constexpr int kSortBytesPerSlot = 8 + 5 * 4 + 4 + 4;   // order key, 5 comparator floats, raw index, permutation
 constexpr uint32_t kSortSentinel = 0xFFFFFFFFu;
 
 __global__ void __launch_bounds__(256)
@@ -863,6 +907,25 @@ image_offsets_kernel(const int *__restrict__ img_kept, int n_img, int *__restric
     if (threadIdx.x == 0) counters[CNT_OUT] = running;
 }
 
+static int g_desc_occ = 1;  // resident describe CTAs per SM (kernel + sm_100 property; set under the init lock)
+
+// Function attributes are per DEVICE: called once for every device a context is created on
+// (b200sift_create, under the init lock), never from a launch path.
+int detect_init_device()
+{
+    const size_t smem = (size_t)kDescWarps * kDescSmemPerWarp;
+    B200_CUDA(cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(describe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int occ = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, describe_kernel, kDescWarps * 32, smem));
+    g_desc_occ = occ < 1 ? 1 : occ;
+    B200_CUDA(cudaFuncSetAttribute(sort_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kSortMaxPerImage * kSortBytesPerSlot));
+    B200_CUDA(cudaFuncSetAttribute(describe_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kDescGenericMaxBins * 32 * (int)sizeof(float)));
+    return 0;
+}
+
 static int ensure_sparse(b200sift_ctx *c, int cand_cap, int loc_cap, int raw_cap)
 {
     size_t cap;
@@ -906,9 +969,17 @@ static int ensure_counters(b200sift_ctx *c, int n_img)
 
 // extrema -> refine -> orientation on the context's pyramid.  Leaves the raw
 // (unsorted) oriented keypoints in c->d_raw and the counters on the host.
-int run_detect(b200sift_ctx *c, const b200sift_params &p, int /*want_scan_order*/)
+int run_detect(b200sift_ctx *c, const b200sift_params &p, int use_dog)
 {
+    // use_dog: extrema + quadratic fit read c->dog_pyr (a caller-supplied dog_images) instead of
+    // forming the differences of the Gaussian layers; orientations always read c->pyr.
     const Pyramid &py = c->pyr;
+    if (use_dog) {
+        const Pyramid &dg = c->dog_pyr;
+        B200_ARG(dg.n_oct == py.n_oct && dg.n_layers == py.n_layers - 1 && dg.n_img == py.n_img);
+        for (int o = 0; o < py.n_oct; ++o) B200_ARG(dg.h[o] == py.h[o] && dg.w[o] == py.w[o]);
+    }
+    const PyrView vd = use_dog ? make_view(c->dog_pyr) : make_view(c);
     B200_ARG(p.num_intervals >= 1 && p.num_intervals + 3 == py.n_layers);
     B200_ARG(p.image_border_width >= 1);
     B200_ARG(p.ori_bins >= 4 && p.ori_bins <= kOriMaxBins);
@@ -938,7 +1009,7 @@ int run_detect(b200sift_ctx *c, const b200sift_params &p, int /*want_scan_order*
             const int sh = py.h[o] - 2 * p.image_border_width, sw = py.w[o] - 2 * p.image_border_width;
             if (sh <= 0 || sw <= 0) continue;
             if (overlap) B200_CUDA(cudaStreamWaitEvent(es, c->ev_oct[o], 0));
-            if (p.num_intervals == 3 && (sw >= 24 || o >= o_merge)) {
+            if (!use_dog && p.num_intervals == 3 && (sw >= 24 || o >= o_merge)) {
                 ExGroup g;
                 g.o_first = o;
                 g.n_oct = 0;
@@ -962,8 +1033,14 @@ int run_detect(b200sift_ctx *c, const b200sift_params &p, int /*want_scan_order*
                 if (o >= o_merge) break;  // the group covered every remaining octave
             } else {
                 dim3 grid((sw + kExTW - 1) / kExTW, (sh + kExTH - 1) / kExTH, py.n_img);
-                extrema_kernel<<<grid, 256, ex_smem, es>>>(v, o, p.image_border_width, p.num_intervals, dp.dog_thresh,
-                                                           c->d_cand, c->cand_cap, c->d_counters);
+                if (use_dog)
+                    extrema_kernel<true><<<grid, 256, ex_smem, es>>>(vd, o, p.image_border_width, p.num_intervals,
+                                                                     dp.dog_thresh, c->d_cand, c->cand_cap,
+                                                                     c->d_counters);
+                else
+                    extrema_kernel<false><<<grid, 256, ex_smem, es>>>(v, o, p.image_border_width, p.num_intervals,
+                                                                      dp.dog_thresh, c->d_cand, c->cand_cap,
+                                                                      c->d_counters);
                 c->launches++;
             }
         }
@@ -975,12 +1052,16 @@ int run_detect(b200sift_ctx *c, const b200sift_params &p, int /*want_scan_order*
         {
             int blocks = (c->cand_cap + 127) / 128;
             if (blocks > c->sm_count * 8) blocks = c->sm_count * 8;
-            refine_kernel<<<blocks, 128, 0, c->stream>>>(v, dp, c->d_cand, c->cand_cap, c->d_loc, c->loc_cap,
-                                                         c->d_counters);
+            if (use_dog)
+                refine_kernel<true><<<blocks, 128, 0, c->stream>>>(vd, dp, c->d_cand, c->cand_cap, c->d_loc,
+                                                                   c->loc_cap, c->d_counters, -1, 0);
+            else
+                refine_kernel<false><<<blocks, 128, 0, c->stream>>>(v, dp, c->d_cand, c->cand_cap, c->d_loc,
+                                                                    c->loc_cap, c->d_counters, -1, 0);
             c->launches++;
             tl_mark(c->stream, "main  refine");
             orient_kernel<<<c->sm_count * 5, kOriWarps * 32, 0, c->stream>>>(v, dp, c->d_loc, c->loc_cap, c->d_raw,
-                                                                             c->raw_cap, c->d_counters);
+                                                                             c->raw_cap, c->d_counters, -1, nullptr);
             c->launches++;
             tl_mark(c->stream, "main  orient");
         }
@@ -1006,23 +1087,22 @@ int run_describe(b200sift_ctx *c, const b200sift_params &p, const RawKeypoint *d
                  uint8_t *d_out)
 {
     if (n <= 0) return 0;
-    B200_ARG(p.window_width == 4 && p.desc_bins == 8);
+    B200_ARG(p.window_width >= 1 && p.desc_bins >= 1 &&
+             p.window_width * p.window_width * p.desc_bins <= kDescGenericMaxBins);
     const PyrView v = make_view(c);
     const DetectParams dp = make_detect_params(p);
+    if (p.window_width != 4 || p.desc_bins != 8) {   // d_out holds n * window_width^2 * desc_bins bytes
+        const int dlen = p.window_width * p.window_width * p.desc_bins;
+        int blocks = n < c->sm_count * 4 ? n : c->sm_count * 4;
+        describe_generic_kernel<<<blocks, 32, (size_t)dlen * 32 * sizeof(float), c->stream>>>(
+            v, dp, p.window_width, p.desc_bins, d_raw, n, converted, d_out);
+        c->launches++;
+        B200_CUDA(cudaGetLastError());
+        return 0;
+    }
     const size_t smem = (size_t)kDescWarps * kDescSmemPerWarp;
-    static bool attr = false;
-    if (!attr) {
-        B200_CUDA(cudaFuncSetAttribute(describe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        B200_CUDA(cudaFuncSetAttribute(describe_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr = true;
-    }
     int blocks = (n + kDescWarps - 1) / kDescWarps;
-    static int occ = 0;  // resident CTAs per SM (13 when the whole 228 KB carve-out is available)
-    if (!occ) {
-        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, describe_kernel, kDescWarps * 32, smem));
-        if (occ < 1) occ = 1;
-    }
-    if (blocks > c->sm_count * occ) blocks = c->sm_count * occ;
+    if (blocks > c->sm_count * g_desc_occ) blocks = c->sm_count * g_desc_occ;
     B200_CHECK(ensure_counters(c, c->pyr.n_img > 0 ? c->pyr.n_img : 1));
     B200_CUDA(cudaMemsetAsync(c->d_counters + CNT_WORK_DESC, 0, sizeof(int32_t), c->stream));
     describe_kernel<<<blocks, kDescWarps * 32, smem, c->stream>>>(v, dp, d_raw, n, converted, d_out,
@@ -1087,12 +1167,7 @@ int run_sort_async(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int de
         B200_CUDA(cudaMemsetAsync(d_cur, 0, sizeof(int) * (n_img + 1), ss));
         int P = 2;
         while (P < max_per) P <<= 1;
-        const size_t smem = (size_t)P * (8 + 5 * 4 + 4 + 4);
-        static size_t attr_smem = 48 * 1024;
-        if (smem > attr_smem) {
-            B200_CUDA(cudaFuncSetAttribute(sort_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_smem = smem;
-        }
+        const size_t smem = (size_t)P * kSortBytesPerSlot;
         // d_pos doubles as the bucketed (unsorted) index list; run_gather's scan rewrites it afterwards
         bucket_kernel<<<blocks, 256, 0, ss>>>(c->d_raw, n_raw, d_off, d_cur, c->d_pos);
         sort_image_kernel<<<n_img, 1024, smem, ss>>>(c->d_raw, d_off, c->d_pos, c->d_sort_idx, scan_order, P, dedupe,
@@ -1164,32 +1239,40 @@ int ensure_sparse_for(b200sift_ctx *c, int n_img, int n_raw)
 // "next" rows f1 / f2
 // ---------------------------------------------------------------------------
 
-// ransac() vote (image_stitching_sift.py:86-111): one thread per candidate
-// shift counts the matches within dist_sq_thresh (float64, as the python
-// floats of the reference); the first maximum wins.
+// ransac() vote (image_stitching_sift.py:86-111): one thread per candidate shift counts the
+// matches within dist_sq_thresh (float64, as the python floats of the reference); the first
+// maximum wins.  The candidate moves are streamed through shared memory in tiles, so the number of
+// matches is not limited by the shared-memory size.
+constexpr int kVoteTile = 1024;
+
 __global__ void __launch_bounds__(256)
-ransac_vote_kernel(const float *__restrict__ m, int n, double thr, int32_t *__restrict__ votes)
+ransac_vote_kernel(const double *__restrict__ m, int n, double thr, int32_t *__restrict__ votes)
 {
-    extern __shared__ double sh[];  // [n][2] candidate moves
-    for (int j = threadIdx.x; j < n; j += 256) {
-        sh[2 * j] = (double)m[4 * j] - (double)m[4 * j + 2];
-        sh[2 * j + 1] = (double)m[4 * j + 1] - (double)m[4 * j + 3];
-    }
-    __syncthreads();
-    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-        const double dxr = sh[2 * i], dyr = sh[2 * i + 1];
-        int cnt = 0;
-        for (int j = 0; j < n; ++j) {
+    __shared__ double sh[2 * kVoteTile];  // candidate moves of the current tile
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    const int ii = min(i, n - 1);
+    const double dxr = m[4 * (size_t)ii] - m[4 * (size_t)ii + 2], dyr = m[4 * (size_t)ii + 1] - m[4 * (size_t)ii + 3];
+    int cnt = 0;
+    for (int j0 = 0; j0 < n; j0 += kVoteTile) {
+        const int nt = min(kVoteTile, n - j0);
+        __syncthreads();
+        for (int j = threadIdx.x; j < nt; j += 256) {
+            sh[2 * j] = m[4 * (size_t)(j0 + j)] - m[4 * (size_t)(j0 + j) + 2];       // :94-96
+            sh[2 * j + 1] = m[4 * (size_t)(j0 + j) + 1] - m[4 * (size_t)(j0 + j) + 3];
+        }
+        __syncthreads();
+        for (int j = 0; j < nt; ++j) {
             const double dx = sh[2 * j] - dxr, dy = sh[2 * j + 1] - dyr;
             cnt += (dx * dx + dy * dy < thr) ? 1 : 0;
         }
-        votes[i] = cnt;
     }
+    if (i < n) votes[i] = cnt;
 }
 
-__global__ void __launch_bounds__(256) ransac_pick_kernel(const int32_t *__restrict__ votes, int n, int32_t *best)
+// first maximum: maximise (votes << 32) | (~index); also hands back the winning move
+__global__ void __launch_bounds__(256)
+ransac_pick_kernel(const int32_t *__restrict__ votes, const double *__restrict__ m, int n, double *__restrict__ out)
 {
-    // first maximum: maximise (votes << 32) | (~index)
     __shared__ unsigned long long red[256];
     unsigned long long k = 0;
     for (int i = threadIdx.x; i < n; i += 256) {
@@ -1203,40 +1286,136 @@ __global__ void __launch_bounds__(256) ransac_pick_kernel(const int32_t *__restr
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        best[0] = (int32_t)(~(uint32_t)(red[0] & 0xffffffffu));
-        best[1] = (int32_t)(red[0] >> 32);
+        const uint32_t best = ~(uint32_t)(red[0] & 0xffffffffu);
+        out[0] = (double)best;
+        out[1] = m[4 * (size_t)best] - m[4 * (size_t)best + 2];
+        out[2] = m[4 * (size_t)best + 1] - m[4 * (size_t)best + 3];
     }
 }
 
-int launch_ransac(b200sift_ctx *c, const float *d_matches, int n, double thr, double *move, int32_t *best)
+int launch_ransac(b200sift_ctx *c, const double *d_matches, int n, double thr, double *move, int32_t *best)
 {
     move[0] = move[1] = 0;
     *best = -1;
     if (n <= 0) return 0;
-    B200_ARG(n <= 12000);  // candidate moves live in shared memory (16 B each)
     size_t cap = c->misc_cap;
-    B200_CHECK(ensure((uint8_t **)&c->d_misc, &cap, (size_t)(n + 8) * sizeof(int32_t)));
+    B200_CHECK(ensure((uint8_t **)&c->d_misc, &cap, (size_t)n * sizeof(int32_t) + 64));
     c->misc_cap = cap;
-    int32_t *votes = (int32_t *)c->d_misc;
-    const size_t smem = (size_t)n * 2 * sizeof(double);
-    static size_t attr_smem = 48 * 1024;
-    if (smem > attr_smem) {
-        B200_CUDA(cudaFuncSetAttribute(ransac_vote_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
-    const int blocks = (n + 255) / 256;
-    ransac_vote_kernel<<<blocks, 256, smem, c->stream>>>(d_matches, n, thr, votes);
-    ransac_pick_kernel<<<1, 256, 0, c->stream>>>(votes, n, votes + n);
+    double *d_out = (double *)c->d_misc;          // 3 doubles, then the votes
+    int32_t *votes = (int32_t *)(d_out + 4);
+    ransac_vote_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_matches, n, thr, votes);
+    ransac_pick_kernel<<<1, 256, 0, c->stream>>>(votes, d_matches, n, d_out);
     c->launches += 2;
     B200_CUDA(cudaGetLastError());
-    int32_t res[2];
-    B200_CUDA(cudaMemcpyAsync(res, votes + n, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
-    float mm[4];
+    double res[3];
+    B200_CUDA(cudaMemcpyAsync(res, d_out, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
     B200_CUDA(cudaStreamSynchronize(c->stream));
-    B200_CUDA(cudaMemcpy(mm, d_matches + 4 * (size_t)res[0], sizeof(mm), cudaMemcpyDeviceToHost));
-    *best = res[0];
-    move[0] = (double)mm[0] - (double)mm[2];
-    move[1] = (double)mm[1] - (double)mm[3];
+    *best = (int32_t)res[0];
+    move[0] = res[1];
+    move[1] = res[2];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Per-call forms of the stage API (sift_impl.py:169-211 and :246-293 as the reference exposes
+// them): the same kernels on a caller's candidates / keypoints, results in input order.
+// ---------------------------------------------------------------------------
+
+// localize_extremum_via_quadratic_fit for n candidates (octave, layer, y, x) on c->pyr (Gaussian
+// layers) or c->dog_pyr (use_dog).  single_octave: the pyramid holds only the candidates' octave.
+// final_layer[i] = -1 where the reference returns None.
+int run_localize_direct(b200sift_ctx *c, const b200sift_params &p, int use_dog, int single_octave,
+                        const int32_t *h_cand, int n, b200sift_keypoint *h_kps, int32_t *h_final_layer)
+{
+    if (n <= 0) return 0;
+    const Pyramid &py = use_dog ? c->dog_pyr : c->pyr;
+    const int n_dog = use_dog ? py.n_layers : py.n_layers - 1;
+    B200_ARG(p.num_intervals >= 1 && n_dog == p.num_intervals + 2 && p.max_iter >= 1);
+    std::vector<Candidate> hc(n);
+    for (int i = 0; i < n; ++i) {
+        const int o = h_cand[4 * i], l = h_cand[4 * i + 1], y = h_cand[4 * i + 2], x = h_cand[4 * i + 3];
+        const int ov = single_octave ? 0 : o;
+        B200_ARG(o >= 0 && o < 31 && ov < py.n_oct && l >= 1 && l <= p.num_intervals);
+        B200_ARG(y >= 1 && y < py.h[ov] - 1 && x >= 1 && x < py.w[ov] - 1);   // the 3x3x3 cube must exist
+        hc[i].img_o_l = ((uint32_t)o << 8) | (uint32_t)l;
+        hc[i].yx = ((uint32_t)y << 16) | (uint32_t)x;
+    }
+    B200_CHECK(ensure_counters(c, 1));
+    B200_CHECK(ensure_sparse(c, n > c->cand_cap ? n : c->cand_cap, n > c->loc_cap ? n : c->loc_cap,
+                             c->raw_cap > 0 ? c->raw_cap : 1024));
+    B200_CUDA(cudaMemcpyAsync(c->d_cand, hc.data(), sizeof(Candidate) * n, cudaMemcpyHostToDevice, c->stream));
+    const PyrView v = make_view(py);
+    const DetectParams dp = make_detect_params(p);
+    const int blocks = (n + 127) / 128;
+    if (use_dog)
+        refine_kernel<true><<<blocks, 128, 0, c->stream>>>(v, dp, c->d_cand, n, c->d_loc, n, c->d_counters, n,
+                                                           single_octave);
+    else
+        refine_kernel<false><<<blocks, 128, 0, c->stream>>>(v, dp, c->d_cand, n, c->d_loc, n, c->d_counters, n,
+                                                            single_octave);
+    c->launches++;
+    B200_CUDA(cudaGetLastError());
+    std::vector<Localized> hl(n);
+    B200_CUDA(cudaMemcpyAsync(hl.data(), c->d_loc, sizeof(Localized) * n, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(cudaStreamSynchronize(c->stream));   // also covers the copy out of `hc`
+    for (int i = 0; i < n; ++i) {
+        const bool ok = hl[i].img_o_l != 0xFFFFFFFFu;
+        b200sift_keypoint k;
+        k.x = ok ? hl[i].x : 0.f; k.y = ok ? hl[i].y : 0.f; k.size = ok ? hl[i].size : 0.f;
+        k.angle = -1.f;                                  // cv2.KeyPoint() default (:206)
+        k.response = ok ? hl[i].response : 0.f;
+        k.octave = ok ? hl[i].octave_packed : 0;
+        h_kps[i] = k;
+        h_final_layer[i] = ok ? (int32_t)(hl[i].img_o_l & 255) : -1;
+    }
+    return 0;
+}
+
+// compute_keypoints_with_orientations for n keypoints on ONE Gaussian image (c->pyr holds it as
+// octave 0 / layer 0); `octave` is the reference's octave argument.  Keypoint i yields counts[i]
+// keypoints at out[i * ori_bins ...], ascending in histogram bin like the reference's list.
+int run_orient_direct(b200sift_ctx *c, const b200sift_params &p, const b200sift_keypoint *h_kps, int n, int octave,
+                      b200sift_keypoint *h_out, int32_t *h_counts)
+{
+    if (n <= 0) return 0;
+    B200_ARG(p.ori_bins >= 4 && p.ori_bins <= kOriMaxBins && octave >= 0 && octave < 30);
+    B200_ARG(c->pyr.n_oct >= 1 && c->pyr.n_layers >= 1 && c->pyr.n_img == 1);
+    const int nb = p.ori_bins;
+    B200_CHECK(ensure_counters(c, 1));
+    B200_CHECK(ensure_sparse(c, c->cand_cap > 0 ? c->cand_cap : 1024, n > c->loc_cap ? n : c->loc_cap,
+                             n * nb > c->raw_cap ? n * nb : c->raw_cap));
+    std::vector<Localized> hl(n);
+    for (int i = 0; i < n; ++i) {
+        hl[i].x = h_kps[i].x; hl[i].y = h_kps[i].y; hl[i].size = h_kps[i].size; hl[i].response = h_kps[i].response;
+        hl[i].octave_packed = h_kps[i].octave;
+        hl[i].img_o_l = (uint32_t)octave << 8;
+        hl[i].order = (uint64_t)i;
+    }
+    B200_CUDA(cudaMemcpyAsync(c->d_loc, hl.data(), sizeof(Localized) * n, cudaMemcpyHostToDevice, c->stream));
+    B200_CUDA(cudaMemsetAsync(c->d_counters, 0, sizeof(int32_t) * CNT_HDR, c->stream));
+    int32_t *d_counts = reinterpret_cast<int32_t *>(c->d_cand);   // scratch: n <= cand_cap * 2
+    B200_ARG((size_t)n * sizeof(int32_t) <= (size_t)c->cand_cap * sizeof(Candidate));
+    const PyrView v = make_view(c);
+    const DetectParams dp = make_detect_params(p);
+    int blocks = (n + kOriWarps - 1) / kOriWarps;
+    if (blocks > c->sm_count * 5) blocks = c->sm_count * 5;
+    orient_kernel<<<blocks, kOriWarps * 32, 0, c->stream>>>(v, dp, c->d_loc, n, c->d_raw, n * nb, c->d_counters, n,
+                                                            d_counts);
+    c->launches++;
+    B200_CUDA(cudaGetLastError());
+    std::vector<RawKeypoint> hr((size_t)n * nb);
+    B200_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
+    B200_CUDA(cudaMemcpyAsync(hr.data(), c->d_raw, sizeof(RawKeypoint) * hr.size(), cudaMemcpyDeviceToHost,
+                              c->stream));
+    B200_CUDA(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < n; ++i)
+        for (int k = 0; k < h_counts[i]; ++k) {
+            const RawKeypoint &r = hr[(size_t)i * nb + k];
+            b200sift_keypoint q;
+            q.x = r.x; q.y = r.y; q.size = r.size; q.angle = r.angle; q.response = r.response;
+            q.octave = r.octave_packed;
+            h_out[(size_t)i * nb + k] = q;
+        }
     return 0;
 }
 

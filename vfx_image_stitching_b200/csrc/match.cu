@@ -7,14 +7,13 @@
 //     fill the GPU; chunks ascend in j, so a strict "<" keeps the lowest j on ties),
 //   * pair_finalize_kernel: acceptance best < desc_thresh (:74), ordered compaction of the match
 //     list and the translation vote, one CTA per image pair,
-//   * a CUDA-core dp4a formulation of the same contraction, kept as a debugging cross-check
-//     (environment B200SIFT_MATCHER=dp4a); it is not used otherwise.
+//   * ratio_accept_kernel: the nearest / second-nearest ratio test of sift_visualizeUI.py:247-257
+//     in exact integers.
 // Descriptors are the 0..255 integers generate_descriptors emits (sift_impl.py:519-524), so
 // |a-b|^2 = |a|^2 + |b|^2 - 2 a.b <= 128*255^2 < 2^24 is exact in int32 (and equals the
 // reference's float32 value bit for bit).
 #include <cub/device/device_scan.cuh>
 #include <limits.h>
-#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 
@@ -25,94 +24,6 @@ int run_match_tc(b200sift_ctx *c, const uint8_t *d_src, int n_imgs, const int *h
                  int n_pairs, const int *h_pairs, int rows_max, int n_chunks_out, int tiles_per_chunk, bool top2,
                  int32_t *d_part);
 void tc_chunking(const b200sift_ctx *c, int rows_max, int nb_max, int n_pairs, int *tiles_per_chunk, int *n_chunks);
-
-static bool use_dp4a()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("B200SIFT_MATCHER");
-        v = (e && strcmp(e, "dp4a") == 0) ? 1 : 0;
-    }
-    return v == 1;
-}
-
-constexpr int kMatchRows = 128;   // A rows per CTA (one per thread)
-constexpr int kMatchTile = 64;    // B rows staged per iteration
-constexpr int kMatchChunk = 512;  // B rows per blockIdx.y (dp4a path)
-
-__global__ void __launch_bounds__(256) norms_kernel(const uint8_t *__restrict__ d, int n, int32_t *__restrict__ out)
-{
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= n) return;
-    const uint4 *p = reinterpret_cast<const uint4 *>(d + (size_t)i * 128);
-    unsigned acc = 0;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        const uint4 v = p[q];
-        acc = __dp4a(v.x, v.x, acc);
-        acc = __dp4a(v.y, v.y, acc);
-        acc = __dp4a(v.z, v.z, acc);
-        acc = __dp4a(v.w, v.w, acc);
-    }
-    out[i] = (int32_t)acc;
-}
-
-// dp4a cross-check: one thread owns one A row in registers and streams B tiles through shared memory
-__global__ void __launch_bounds__(kMatchRows)
-match_pairs_kernel(const uint8_t *__restrict__ descA, const uint8_t *__restrict__ descB,
-                   const int32_t *__restrict__ nrmB_all, const PairDesc *__restrict__ pd, int n_chunks_max,
-                   int rows_max, int32_t *__restrict__ part /*[pair][rows_max][n_chunks_max][3]*/)
-{
-    __shared__ uint4 b_s[kMatchTile * 8];
-    __shared__ int32_t nb_s[kMatchTile];
-    const PairDesc P = pd[blockIdx.z];
-    const int chunk = blockIdx.y;
-    if ((int)(blockIdx.x * kMatchRows) >= P.nA) return;
-    const int j_begin = chunk * kMatchChunk, j_end = min(P.nB, j_begin + kMatchChunk);
-    const uint8_t *A = descA + (size_t)P.offA * 128, *B = descB + (size_t)P.offB * 128;
-    const int32_t *nrmB = nrmB_all + P.offB;
-    const int i = blockIdx.x * kMatchRows + threadIdx.x;
-    uint32_t a[32];
-    unsigned na = 0;
-    {
-        const int ii = min(i, P.nA - 1);
-        const uint4 *p = reinterpret_cast<const uint4 *>(A + (size_t)ii * 128);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const uint4 v = p[q];
-            a[4 * q] = v.x; a[4 * q + 1] = v.y; a[4 * q + 2] = v.z; a[4 * q + 3] = v.w;
-        }
-#pragma unroll
-        for (int q = 0; q < 32; ++q) na = __dp4a(a[q], a[q], na);
-    }
-    int b1 = INT_MAX, b2 = INT_MAX, bi = -1;
-    for (int j0 = j_begin; j0 < j_end; j0 += kMatchTile) {
-        const int nt = min(kMatchTile, j_end - j0);
-        __syncthreads();
-        for (int t = threadIdx.x; t < nt * 8; t += kMatchRows)
-            b_s[t] = reinterpret_cast<const uint4 *>(B + (size_t)j0 * 128)[t];
-        for (int t = threadIdx.x; t < nt; t += kMatchRows) nb_s[t] = nrmB[j0 + t];
-        __syncthreads();
-        for (int t = 0; t < nt; ++t) {
-            unsigned dot = 0;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const uint4 v = b_s[t * 8 + q];
-                dot = __dp4a(a[4 * q], v.x, dot);
-                dot = __dp4a(a[4 * q + 1], v.y, dot);
-                dot = __dp4a(a[4 * q + 2], v.z, dot);
-                dot = __dp4a(a[4 * q + 3], v.w, dot);
-            }
-            const int d = (int)na + nb_s[t] - 2 * (int)dot;
-            if (d < b1) { b2 = b1; b1 = d; bi = j0 + t; }
-            else if (d < b2) b2 = d;
-        }
-    }
-    if (i < P.nA) {
-        int32_t *o = part + (((size_t)blockIdx.z * rows_max + i) * n_chunks_max + chunk) * 3;
-        o[0] = bi; o[1] = b1; o[2] = b2;
-    }
-}
 
 // per-chunk (best j, best d, second d) -> global top-2; chunks ascend in j
 __global__ void __launch_bounds__(256)
@@ -140,27 +51,6 @@ int run_match(b200sift_ctx *c, const uint8_t *dA, int nA, const uint8_t *dB, int
 {
     if (nA <= 0) return 0;
     size_t cap;
-    if (use_dp4a()) {
-        const int n_chunks = nB > 0 ? (nB + kMatchChunk - 1) / kMatchChunk : 1;
-        cap = c->nrmB_cap;
-        B200_CHECK(ensure(&c->d_nrmB, &cap, (size_t)(nB > 0 ? nB : 1)));
-        c->nrmB_cap = cap;
-        cap = c->mout_cap;
-        B200_CHECK(ensure(&c->d_mout, &cap, (size_t)nA * n_chunks * 3 + 16));
-        c->mout_cap = cap;
-        PairDesc pd{0, nA, 0, nB};
-        PairDesc *d_pd = reinterpret_cast<PairDesc *>(c->d_mout + (size_t)nA * n_chunks * 3);
-        B200_CUDA(cudaMemcpyAsync(d_pd, &pd, sizeof(pd), cudaMemcpyHostToDevice, c->stream));
-        B200_CUDA(cudaStreamSynchronize(c->stream));
-        if (nB > 0) norms_kernel<<<(nB + 255) / 256, 256, 0, c->stream>>>(dB, nB, c->d_nrmB);
-        dim3 grid((nA + kMatchRows - 1) / kMatchRows, n_chunks, 1);
-        match_pairs_kernel<<<grid, kMatchRows, 0, c->stream>>>(dA, dB, c->d_nrmB, d_pd, n_chunks, nA, c->d_mout);
-        match_merge_kernel<<<(nA + 255) / 256, 256, 0, c->stream>>>(c->d_mout, nA, n_chunks, d_best_idx, d_best_d2,
-                                                                    d_second_d2);
-        c->launches += 3;
-        B200_CUDA(cudaGetLastError());
-        return 0;
-    }
     // tensor-core path: A and B become "image" 0 and 1 of one packed buffer
     int tpc, n_chunks;
     tc_chunking(c, nA, nB, 1, &tpc, &n_chunks);
@@ -298,10 +188,8 @@ int run_match_pairs(b200sift_ctx *c, int n_pairs, const int *h_pairs, int thresh
         rows_max = h_pd[p].nA > rows_max ? h_pd[p].nA : rows_max;
         nb_max = h_pd[p].nB > nb_max ? h_pd[p].nB : nb_max;
     }
-    const int n_total = c->img_off.empty() ? 0 : c->img_off.back();
     int tpc = 1, n_chunks;
-    if (use_dp4a()) n_chunks = nb_max > 0 ? (nb_max + kMatchChunk - 1) / kMatchChunk : 1;
-    else tc_chunking(c, rows_max, nb_max, n_pairs, &tpc, &n_chunks);
+    tc_chunking(c, rows_max, nb_max, n_pairs, &tpc, &n_chunks);
     size_t cap = c->mout_cap;
     B200_CHECK(ensure(&c->d_mout, &cap, (size_t)n_pairs * rows_max * n_chunks * 3));
     c->mout_cap = cap;
@@ -322,17 +210,7 @@ int run_match_pairs(b200sift_ctx *c, int n_pairs, const int *h_pairs, int thresh
     c->pair_n = n_pairs;
     c->d_pair_res = res; c->d_pair_ia = m_ia; c->d_pair_ib = m_ib; c->d_pair_xy = m_xy;
     B200_CUDA(cudaMemcpyAsync(pd, h_pd.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, c->stream));
-    if (use_dp4a()) {
-        cap = c->nrmB_cap;
-        B200_CHECK(ensure(&c->d_nrmB, &cap, (size_t)(n_total > 0 ? n_total : 1)));
-        c->nrmB_cap = cap;
-        if (n_total > 0) norms_kernel<<<(n_total + 255) / 256, 256, 0, c->stream>>>(c->d_desc, n_total, c->d_nrmB);
-        dim3 grid((rows_max + kMatchRows - 1) / kMatchRows, n_chunks, n_pairs);
-        match_pairs_kernel<<<grid, kMatchRows, 0, c->stream>>>(c->d_desc, c->d_desc, c->d_nrmB, pd, n_chunks, rows_max,
-                                                              c->d_mout);
-        c->launches += 2;
-        B200_CUDA(cudaStreamSynchronize(c->stream));  // h_pd is read by the async copy above
-    } else {
+    {
         std::vector<int> off(n_img), cnt(n_img);
         for (int i = 0; i < n_img; ++i) { off[i] = c->img_off[i]; cnt[i] = c->img_off[i + 1] - c->img_off[i]; }
         B200_CHECK(run_match_tc(c, c->d_desc, n_img, off.data(), cnt.data(), n_pairs, h_pairs, rows_max, n_chunks, tpc,
@@ -372,6 +250,23 @@ accept_scatter_kernel(const int32_t *__restrict__ best_idx, const uint32_t *__re
     xyxy[4 * d] = kA[i].x; xyxy[4 * d + 1] = kA[i].y; xyxy[4 * d + 2] = kB[j].x; xyxy[4 * d + 3] = kB[j].y;
 }
 
+// exclusive scan of c->d_keep[0..n) into c->d_pos on the context stream
+static int scan_keep(b200sift_ctx *c, int n)
+{
+    size_t tmp = 0;
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->d_keep, c->d_pos, n, c->stream));
+    if (tmp > c->cub_tmp_cap) {
+        B200_CUDA(cudaStreamSynchronize(c->stream));
+        if (c->d_cub_tmp) cudaFree(c->d_cub_tmp);
+        c->d_cub_tmp = nullptr;
+        B200_CUDA(cudaMalloc(&c->d_cub_tmp, tmp + 1024));
+        c->cub_tmp_cap = tmp + 1024;
+    }
+    tmp = c->cub_tmp_cap;
+    B200_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub_tmp, tmp, c->d_keep, c->d_pos, n, c->stream));
+    return 0;
+}
+
 // best_idx / best_d2 (device) -> ordered accepted list (device); *d_count receives n
 int run_accept(b200sift_ctx *c, const int32_t *d_idx, const int32_t *d_d2, int nA, int thresh,
                const b200sift_keypoint *kA, const b200sift_keypoint *kB, int32_t *d_ia, int32_t *d_ib,
@@ -381,18 +276,54 @@ int run_accept(b200sift_ctx *c, const int32_t *d_idx, const int32_t *d_d2, int n
     B200_ARG(nA <= c->raw_cap);
     const int blocks = (nA + 255) / 256;
     accept_flag_kernel<<<blocks, 256, 0, c->stream>>>(d_idx, d_d2, nA, thresh, c->d_keep);
-    size_t tmp = 0;
-    B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->d_keep, c->d_pos, nA, c->stream));
-    if (tmp > c->cub_tmp_cap) {
-        if (c->d_cub_tmp) cudaFree(c->d_cub_tmp);
-        c->d_cub_tmp = nullptr;
-        B200_CUDA(cudaMalloc(&c->d_cub_tmp, tmp + 1024));
-        c->cub_tmp_cap = tmp + 1024;
-    }
-    tmp = c->cub_tmp_cap;
-    B200_CUDA(cub::DeviceScan::ExclusiveSum(c->d_cub_tmp, tmp, c->d_keep, c->d_pos, nA, c->stream));
+    B200_CHECK(scan_keep(c, nA));
     accept_scatter_kernel<<<blocks, 256, 0, c->stream>>>(d_idx, c->d_keep, c->d_pos, nA, kA, kB, d_ia, d_ib, d_xyxy,
                                                          d_count);
+    c->launches += 3;
+    B200_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Nearest / second-nearest ratio test (sift_visualizeUI.py:247-257: knnMatch(k=2), keep m when
+// m.distance < 0.7 * n.distance).  The reference gets its two neighbours from approximate FLANN
+// KD-trees; here they are the exact ones, and the test is evaluated on the squared integer
+// distances: sqrt(d1) < (num/den) sqrt(d2)  <=>  den^2 d1 < num^2 d2  (64-bit, exact).  A row
+// without a second neighbour (nB < 2) is rejected.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ratio_flag_kernel(const int32_t *__restrict__ best_idx, const int32_t *__restrict__ d1, const int32_t *__restrict__ d2,
+                  int nA, long long num2, long long den2, uint32_t *__restrict__ keep)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= nA) return;
+    const bool ok = best_idx[i] != -1 && d2[i] != INT_MAX && den2 * (long long)d1[i] < num2 * (long long)d2[i];
+    keep[i] = ok ? 1u : 0u;
+}
+
+__global__ void __launch_bounds__(256)
+ratio_scatter_kernel(const int32_t *__restrict__ best_idx, const uint32_t *__restrict__ keep,
+                     const uint32_t *__restrict__ pos, int nA, int32_t *__restrict__ ia, int32_t *__restrict__ ib,
+                     int32_t *__restrict__ count)
+{
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= nA) return;
+    if (i == nA - 1) *count = (int32_t)(pos[i] + keep[i]);
+    if (!keep[i]) return;
+    ia[pos[i]] = i;
+    ib[pos[i]] = best_idx[i];
+}
+
+int run_ratio_accept(b200sift_ctx *c, const int32_t *d_idx, const int32_t *d_d1, const int32_t *d_d2, int nA, int num,
+                     int den, int32_t *d_ia, int32_t *d_ib, int32_t *d_count)
+{
+    if (nA <= 0) return 0;
+    B200_CHECK(ensure_sparse_for(c, 1, nA));   // d_keep / d_pos hold nA flags
+    const int blocks = (nA + 255) / 256;
+    ratio_flag_kernel<<<blocks, 256, 0, c->stream>>>(d_idx, d_d1, d_d2, nA, (long long)num * num, (long long)den * den,
+                                                     c->d_keep);
+    B200_CHECK(scan_keep(c, nA));
+    ratio_scatter_kernel<<<blocks, 256, 0, c->stream>>>(d_idx, c->d_keep, c->d_pos, nA, d_ia, d_ib, d_count);
     c->launches += 3;
     B200_CUDA(cudaGetLastError());
     return 0;

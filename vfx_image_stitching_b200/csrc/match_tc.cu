@@ -311,6 +311,17 @@ match_tc_kernel(const uint8_t *__restrict__ packed, const int32_t *__restrict__ 
 
 constexpr size_t kTcSmemBytes = kTcABytes + (size_t)kTcStages * kTcBBytes + 2 * kTcN * 4 + 16 * 8 + 64;
 
+// Function attributes are per DEVICE: called once for every device a context is created on
+// (b200sift_create, under the init lock), never from a launch path.
+int match_init_device()
+{
+    B200_CUDA(cudaFuncSetAttribute(match_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)kTcSmemBytes));
+    B200_CUDA(cudaFuncSetAttribute(match_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)kTcSmemBytes));
+    return 0;
+}
+
 // Pack `n_imgs` descriptor sets (rows of c->d_desc or of an explicit source) and run every pair.
 // part layout = the one pair_finalize_kernel / match_merge_kernel read.
 int run_match_tc(b200sift_ctx *c, const uint8_t *d_src, int n_imgs, const int *h_src_off, const int *h_n,
@@ -355,14 +366,8 @@ int run_match_tc(b200sift_ctx *c, const uint8_t *d_src, int n_imgs, const int *h
         pack_kernel<<<pg, 256, 0, c->stream>>>(d_src, d_imgs, packed, nrm);
         c->launches++;
     }
-    static bool attr = false;
-    if (!attr) {
-        B200_CUDA(cudaFuncSetAttribute(match_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kTcSmemBytes));
-        B200_CUDA(cudaFuncSetAttribute(match_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kTcSmemBytes));
-        attr = true;
-    }
+    c->last_tiles_per_chunk = tiles_per_chunk;
+    c->last_n_chunks = n_chunks_out;
     dim3 grid((rows_max + kTcM - 1) / kTcM, n_chunks_out, n_pairs);
     if (top2)
         match_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, c->stream>>>(packed, nrm, d_tp, tiles_per_chunk,

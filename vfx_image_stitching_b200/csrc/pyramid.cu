@@ -1,5 +1,5 @@
 // Dense front-end of the SIFT path: grey conversion + 2x upsample, separable
-// Gaussian blur (HBM-bound strip kernel + generic tile kernel), octave
+// Gaussian blur (HBM-bound packed ring kernel + generic tile kernel), octave
 // decimation, DoG materialisation for the stage API.
 //
 // Replaces (all in /root/reference): sift_impl.py:27-29 (cv2.cvtColor + float
@@ -13,17 +13,12 @@
 
 namespace b200 {
 
-// Up to 16 tap sets (centre..R) resident in constant memory; a launch names
-// its set.  Set 15 is reserved for the stand-alone blur entry point.
-__constant__ float c_taps[16][kMaxBlurRadius + 1];
-
-struct TapCache {
-    double sigma[16];
-    int radius[16];
-    bool valid[16];
-    float taps[16][kMaxBlurRadius + 1];  // host copy: the strip kernel takes its taps as a parameter
-};
-static TapCache g_taps[16];  // per device ordinal
+// Up to 16 tap sets (centre..R) per CONTEXT, in global memory (b200sift_ctx::d_taps, host mirror and
+// sigma cache in b200sift_ctx::taps): contexts that run concurrently on one GPU with different
+// sigmas cannot overwrite each other's sets, and an update is an ordinary stream-ordered copy.
+// A launch names its set; set 15 is reserved for the stand-alone blur entry point.  The packed ring
+// kernel takes its taps as a kernel parameter (uniform-register operands), the tile / tail kernels
+// read them from the table.
 
 // cv2.getGaussianKernel(ksize, sigma, CV_32F) with ksize = cvRound(8*sigma+1)|1
 // (the CV_32F branch of cv::createGaussianKernels): taps = float(exp(-x^2/2s^2)/sum).
@@ -45,7 +40,7 @@ static int gaussian_taps(double sigma, float *taps /*centre..R*/)
 
 static int upload_taps(b200sift_ctx *c, int set, double sigma, int *radius)
 {
-    TapCache &tc = g_taps[c->device & 15];
+    TapCache &tc = c->taps;
     if (tc.valid[set] && tc.sigma[set] == sigma) {
         *radius = tc.radius[set];
         return 0;
@@ -56,12 +51,15 @@ static int upload_taps(b200sift_ctx *c, int set, double sigma, int *radius)
         set_error("sigma %.3f needs a blur radius > %d", sigma, kMaxBlurRadius);
         return B200SIFT_EARG;
     }
-    // Synchronous copy (pageable source buffer lives on this stack frame); ordered
-    // after earlier launches that may still read the set.
-    B200_CUDA(cudaStreamSynchronize(c->stream));
-    B200_CUDA(cudaMemcpyToSymbol(c_taps, taps, sizeof(taps), (size_t)set * sizeof(taps)));
-    tc.valid[set] = true;
+    if (!c->d_taps) B200_CUDA(cudaMalloc((void **)&c->d_taps, sizeof(tc.taps)));
+    // The host mirror of a set is rewritten below while an earlier asynchronous copy of the same set
+    // could still be reading it: wait for the stream first (rare: only when a sigma changes).
+    if (tc.valid[set]) B200_CUDA(cudaStreamSynchronize(c->stream));
     memcpy(tc.taps[set], taps, sizeof(taps));
+    // stream-ordered: later launches of this context see the new set, earlier ones the old
+    B200_CUDA(cudaMemcpyAsync(c->d_taps + (size_t)set * (kMaxBlurRadius + 1), tc.taps[set], sizeof(taps),
+                              cudaMemcpyHostToDevice, c->stream));
+    tc.valid[set] = true;
     tc.sigma[set] = sigma;
     tc.radius[set] = r;
     *radius = r;
@@ -166,14 +164,13 @@ int launch_gray_upsample(b200sift_ctx *c, const void *d_in, size_t img_stride_by
     return 0;
 }
 
-#include "blur_strip.cuh"
 #include "blur_ring.cuh"
 
 // Generic tile blur: any radius <= kMaxBlurRadius, any (tiny) image.  32x32 output tile, halo tile in
-// shared memory, same arithmetic as the strip kernel.  All 256 threads of the CTA call it together.
+// shared memory, k0*c + sum k[k]*(a[+k]+a[-k]) with fmaf.  All 256 threads of the CTA call it together.
 __device__ __forceinline__ void blur_tile(const float *__restrict__ src, float *__restrict__ dst,
                                           float *__restrict__ dst2, int h, int w, int pitch, int h2, int w2,
-                                          int pitch2, int R, int tapset, int x0, int y0, float *smem)
+                                          int pitch2, int R, const float *__restrict__ taps, int x0, int y0, float *smem)
 {
     constexpr int T = 32;
     const int IW = T + 2 * R;
@@ -185,7 +182,6 @@ __device__ __forceinline__ void blur_tile(const float *__restrict__ src, float *
         in_s[i] = __ldcg(&src[(size_t)reflect101(y0 - R + yy, h) * pitch + reflect101(x0 - R + xx, w)]);
     }
     __syncthreads();
-    const float *taps = c_taps[tapset];
     for (int i = threadIdx.x; i < IW * T; i += 256) {
         const int yy = i / T, cx = i - yy * T;
         const float *p = in_s + yy * IW + cx + R;
@@ -210,13 +206,14 @@ __device__ __forceinline__ void blur_tile(const float *__restrict__ src, float *
 
 __global__ void __launch_bounds__(256)
 blur_tile_kernel(const float *__restrict__ src, float *__restrict__ dst, float *__restrict__ dst2, int h, int w,
-                 int pitch, size_t img_stride, int h2, int w2, int pitch2, size_t img_stride2, int R, int tapset)
+                 int pitch, size_t img_stride, int h2, int w2, int pitch2, size_t img_stride2, int R,
+                 const float *__restrict__ taps)
 {
     extern __shared__ __align__(16) float smem[];
     src += (size_t)blockIdx.z * img_stride;
     dst += (size_t)blockIdx.z * img_stride;
     if (dst2) dst2 += (size_t)blockIdx.z * img_stride2;
-    blur_tile(src, dst, dst2, h, w, pitch, h2, w2, pitch2, R, tapset, blockIdx.x * 32, blockIdx.y * 32, smem);
+    blur_tile(src, dst, dst2, h, w, pitch, h2, w2, pitch2, R, taps, blockIdx.x * 32, blockIdx.y * 32, smem);
 }
 
 // ---------------------------------------------------------------------------
@@ -228,10 +225,11 @@ blur_tile_kernel(const float *__restrict__ src, float *__restrict__ dst, float *
 // Each thread produces 4 adjacent outputs per pass from 4+2R shared-memory values; the column pass
 // writes the new layer to HBM, back into A for the next blur of the chain (sift_impl.py:90-92) and,
 // for layer n_layers-3, its [::2, ::2] decimation as layer 0 of the next octave (:95-96).
-// Same arithmetic as the strip kernel (k0*c + sum k[k]*(a[+k]+a[-k]), fmaf, BORDER_REFLECT_101).
+// Arithmetic: k0*c + sum k[k]*(a[+k]+a[-k]), fmaf, BORDER_REFLECT_101.
 // ---------------------------------------------------------------------------
 struct TailArgs {
     float *base;                 // pyramid allocation
+    const float *taps;           // the context's tap table (set l = layer l)
     size_t oct_off[kMaxOctaves]; // float offset of octave o
     int h[kMaxOctaves], w[kMaxOctaves], pitch[kMaxOctaves];
     int radius[kMaxLayers];      // per layer (tap set index = layer)
@@ -351,7 +349,7 @@ __global__ void __launch_bounds__(kTailThreads) pyramid_tail_kernel(const __grid
         __syncthreads();
         for (int l = 1; l < a.n_layers; ++l) {
             const int R = a.radius[l];
-            const float *taps = c_taps[l];
+            const float *taps = a.taps + (size_t)l * (kMaxBlurRadius + 1);
             float *dst = a.base + a.oct_off[o] + ((size_t)l * a.n_img + img) * istride;
             float *dst2 = nullptr;
             int h2 = 0, w2 = 0, pitch2 = 0;
@@ -373,55 +371,43 @@ __global__ void __launch_bounds__(kTailThreads) pyramid_tail_kernel(const __grid
     }
 }
 
-template <int R>
-static int launch_strip(b200sift_ctx *c, const float *src, float *dst, float *dst2, int n_img, int h, int w,
-                        int pitch, size_t img_stride, int h2, int w2, int pitch2, size_t img_stride2, int tapset)
+// Resident CTAs per SM of every ring instantiation (a property of the kernel and of sm_100, the
+// same on every device): filled once by pyramid_init_device under the library's init lock.
+template <int R, int STAGES>
+struct RingOcc { static int occ; };
+template <int R, int STAGES>
+int RingOcc<R, STAGES>::occ = 1;
+
+template <int R, int STAGES>
+static int ring_setup()
 {
-    const size_t smem = strip_smem_bytes<R>();
-    static int occ = 0;  // resident CTAs per SM of this instantiation
-    if (!occ) {
-        B200_CUDA(cudaFuncSetAttribute(blur_strip_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blur_strip_kernel<R>, 256, smem));
-        if (occ < 1) occ = 1;
-    }
-    const int strips = (w + kStripW - 1) / kStripW;
-    const int cols = strips * n_img;
-    // One wave if possible: the largest segment count whose CTAs are all co-resident (segments of
-    // >= 32 rows); larger problems run several waves of 64-row segments (y-halo re-read 2R/64).
-    const int slots = c->sm_count * occ;
-    int n_seg = slots / cols;
-    int seg;
-    if (n_seg >= 1) {
-        seg = (h + n_seg - 1) / n_seg;
-        seg = ((seg + kStripBR - 1) / kStripBR) * kStripBR;
-        if (seg < 32) seg = 32;
-    } else {
-        seg = 64;
-    }
-    if (seg > 4096) seg = 4096;
-    dim3 grid(strips, (h + seg - 1) / seg, n_img);
-    BlurTaps<R> taps;
-    memcpy(taps.t, g_taps[c->device & 15].taps[tapset], sizeof(taps.t));
-    blur_strip_kernel<R><<<grid, 256, smem, c->blur_stream ? c->blur_stream : c->stream>>>(src, dst, dst2, h, w, pitch, img_stride, h2, w2, pitch2,
-                                                         img_stride2, seg, taps);
-    c->launches++;
-    B200_CUDA(cudaGetLastError());
+    const size_t smem = RingCfg<R, STAGES>::smem;
+    B200_CUDA(cudaFuncSetAttribute(blur_ring_kernel<R, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA(cudaFuncSetAttribute(blur_ring_kernel<R, STAGES>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int occ = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blur_ring_kernel<R, STAGES>, kRingThreads, smem));
+    RingOcc<R, STAGES>::occ = occ < 1 ? 1 : occ;
     return 0;
 }
 
-template <int R, int STAGES>
-static int ring_occupancy(int *occ_out)
+template <int R>
+struct RingDepth { static constexpr int S = (R >= 12) ? 2 : 3; };
+
+constexpr size_t kTileSmemMax = (size_t)((32 + 2 * kMaxBlurRadius) * (32 + 2 * kMaxBlurRadius) +
+                                         (32 + 2 * kMaxBlurRadius) * 32) * sizeof(float);
+constexpr size_t kTailSmemMax = 200 * 1024;
+
+// Function attributes are per DEVICE: called once for every device a context is created on
+// (b200sift_create, under the init lock), never from a launch path.
+int pyramid_init_device()
 {
-    static int occ = 0;  // resident CTAs per SM of this instantiation
-    if (!occ) {
-        const size_t smem = RingCfg<R, STAGES>::smem;
-        B200_CUDA(cudaFuncSetAttribute(blur_ring_kernel<R, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-        B200_CUDA(cudaFuncSetAttribute(blur_ring_kernel<R, STAGES>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, blur_ring_kernel<R, STAGES>, kRingThreads, smem));
-        if (occ < 1) occ = 1;
-    }
-    *occ_out = occ;
+    B200_CHECK((ring_setup<5, RingDepth<5>::S>()));
+    B200_CHECK((ring_setup<6, RingDepth<6>::S>()));
+    B200_CHECK((ring_setup<8, RingDepth<8>::S>()));
+    B200_CHECK((ring_setup<10, RingDepth<10>::S>()));
+    B200_CHECK((ring_setup<13, RingDepth<13>::S>()));
+    B200_CUDA(cudaFuncSetAttribute(blur_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTileSmemMax));
+    B200_CUDA(cudaFuncSetAttribute(pyramid_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemMax));
     return 0;
 }
 
@@ -430,11 +416,9 @@ static int launch_ring_s(b200sift_ctx *c, const float *src, float *dst, float *d
                          int pitch, size_t img_stride, int h2, int w2, int pitch2, size_t img_stride2, int tapset,
                          int seg)
 {
-    int occ;
-    B200_CHECK((ring_occupancy<R, STAGES>(&occ)));
     dim3 grid((w + kRingW - 1) / kRingW, (h + seg - 1) / seg, n_img);
     BlurTaps<R> taps;
-    memcpy(taps.t, g_taps[c->device & 15].taps[tapset], sizeof(taps.t));
+    memcpy(taps.t, c->taps.taps[tapset], sizeof(taps.t));
     blur_ring_kernel<R, STAGES><<<grid, kRingThreads, RingCfg<R, STAGES>::smem,
                                   c->blur_stream ? c->blur_stream : c->stream>>>(
         src, dst, dst2, h, w, pitch, img_stride, h2, w2, pitch2, img_stride2, seg, taps);
@@ -455,11 +439,9 @@ template <int R>
 static int launch_ring(b200sift_ctx *c, const float *src, float *dst, float *dst2, int n_img, int h, int w,
                        int pitch, size_t img_stride, int h2, int w2, int pitch2, size_t img_stride2, int tapset)
 {
-    constexpr int SDEEP = (R >= 12) ? 2 : 3;
-    int occ_deep = 1;
-    B200_CHECK((ring_occupancy<R, SDEEP>(&occ_deep)));
+    constexpr int SDEEP = RingDepth<R>::S;
     const int cols = ((w + kRingW - 1) / kRingW) * n_img;
-    const int slots = c->sm_count * occ_deep;
+    const int slots = c->sm_count * RingOcc<R, SDEEP>::occ;
     const int n1 = slots / cols;
     int seg = 256;
     if (n1 >= 1 && (long long)cols * ((h + 255) / 256) < slots) {  // 256-row segments would not even fill one wave
@@ -467,73 +449,41 @@ static int launch_ring(b200sift_ctx *c, const float *src, float *dst, float *dst
         seg = ((seg + kRingBR - 1) / kRingBR) * kRingBR;
         if (seg < 32) seg = 32;
     }
-    {
-        static const char *e = getenv("B200SIFT_RING_SEG");  // experiment hook: force the segment height
-        if (e && atoi(e) >= 8) seg = (atoi(e) + 7) & ~7;
-    }
     return launch_ring_s<R, SDEEP>(c, src, dst, dst2, n_img, h, w, pitch, img_stride, h2, w2, pitch2, img_stride2,
                                    tapset, seg);
-}
-
-// B200SIFT_BLUR=strip selects the scalar strip kernel (kept as a cross-check of the packed ring kernel).
-static bool use_ring_blur()
-{
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("B200SIFT_BLUR");
-        v = (e && !strcmp(e, "strip")) ? 0 : 1;
-    }
-    return v == 1;
 }
 
 static int launch_blur_set(b200sift_ctx *c, const float *src, float *dst, int n_img, int h, int w, int pitch,
                            size_t img_stride, int R, int tapset, float *dst2, int h2, int w2, int pitch2,
                            size_t img_stride2)
 {
-    // 16 B loads from src, 8 B (ring kernel) stores to dst: both row-aligned
-    const bool strip_ok = (w >= 96) && (h >= 32) && (pitch % 4 == 0) &&
-                          ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
-                          ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (img_stride % 4 == 0);
-    if (strip_ok) {
-        if (use_ring_blur()) {
-            switch (R) {
+    // ring kernel: 16 B loads from src, 8 B stores to dst, both row-aligned; the radii of the
+    // reference's sigma chain (sift_impl.py:66-79 with sigma = 1.6, num_intervals = 3, and the base blur)
+    const bool ring_ok = (w >= 96) && (h >= 32) && (pitch % 4 == 0) &&
+                         ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (img_stride % 4 == 0);
+    if (ring_ok) {
+        switch (R) {
 #define B200_RING(RR)                                                                                         \
     case RR:                                                                                                  \
         return launch_ring<RR>(c, src, dst, dst2, n_img, h, w, pitch, img_stride, h2, w2, pitch2, img_stride2, \
                                tapset);
-                B200_RING(5)
-                B200_RING(6)
-                B200_RING(8)
-                B200_RING(10)
-                B200_RING(13)
+            B200_RING(5)
+            B200_RING(6)
+            B200_RING(8)
+            B200_RING(10)
+            B200_RING(13)
 #undef B200_RING
-                default: break;
-            }
-        }
-        switch (R) {
-#define B200_STRIP(RR)                                                                                         \
-    case RR:                                                                                                   \
-        return launch_strip<RR>(c, src, dst, dst2, n_img, h, w, pitch, img_stride, h2, w2, pitch2, img_stride2, \
-                                tapset);
-            B200_STRIP(5)
-            B200_STRIP(6)
-            B200_STRIP(8)
-            B200_STRIP(10)
-            B200_STRIP(13)
-#undef B200_STRIP
             default: break;
         }
     }
+    // any other radius / tiny or unaligned image: generic tile kernel
     const int IW = 32 + 2 * R;
     const size_t smem = (size_t)(IW * IW + IW * 32) * sizeof(float);
-    static size_t attr_smem = 48 * 1024;
-    if (smem > attr_smem) {
-        B200_CUDA(cudaFuncSetAttribute(blur_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
     dim3 grid((w + 31) / 32, (h + 31) / 32, n_img);
-    blur_tile_kernel<<<grid, 256, smem, c->blur_stream ? c->blur_stream : c->stream>>>(src, dst, dst2, h, w, pitch, img_stride, h2, w2, pitch2,
-                                                     img_stride2, R, tapset);
+    blur_tile_kernel<<<grid, 256, smem, c->blur_stream ? c->blur_stream : c->stream>>>(
+        src, dst, dst2, h, w, pitch, img_stride, h2, w2, pitch2, img_stride2, R,
+        c->d_taps + (size_t)tapset * (kMaxBlurRadius + 1));
     c->launches++;
     B200_CUDA(cudaGetLastError());
     return 0;
@@ -552,11 +502,15 @@ int launch_blur(b200sift_ctx *c, const float *src, float *dst, int n_img, int h,
 // ---------------------------------------------------------------------------
 int pyramid_layout(b200sift_ctx *c, int n_img, int h0, int w0, int n_oct, int n_layers)
 {
+    c->oct_events_valid = false;
+    return pyramid_layout_into(c->pyr, n_img, h0, w0, n_oct, n_layers);
+}
+
+int pyramid_layout_into(Pyramid &p, int n_img, int h0, int w0, int n_oct, int n_layers)
+{
     B200_ARG(n_img >= 1 && h0 >= 1 && w0 >= 1);
     B200_ARG(n_oct >= 1 && n_oct <= kMaxOctaves);
-    B200_ARG(n_layers >= 4 && n_layers <= kMaxLayers);
-    Pyramid &p = c->pyr;
-    c->oct_events_valid = false;
+    B200_ARG(n_layers >= 1 && n_layers <= kMaxLayers);
     p.n_img = n_img;
     p.n_oct = n_oct;
     p.n_layers = n_layers;
@@ -607,16 +561,7 @@ int build_octaves(b200sift_ctx *c, const double *sigmas)
         const int h0 = p.h[o_tail], w0 = p.w[o_tail];
         (void)w0;
         tail_smem = tail_smem_bytes(h0);
-        if (tail_smem > 200 * 1024 || max_r > kTailRm) {
-            o_tail = p.n_oct;
-        } else {
-            static size_t attr_smem = 48 * 1024;
-            if (tail_smem > attr_smem) {
-                B200_CUDA(cudaFuncSetAttribute(pyramid_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)tail_smem));
-                attr_smem = tail_smem;
-            }
-        }
+        if (tail_smem > kTailSmemMax || max_r > kTailRm) o_tail = p.n_oct;
     }
     // Critical path of the pyramid: layers 1..n-3 of octave o, whose last one seeds octave o+1
     // (sift_impl.py:95-96).  The remaining layers of octave o feed nothing downstream but the
@@ -656,6 +601,7 @@ int build_octaves(b200sift_ctx *c, const double *sigmas)
     if (o_tail < p.n_oct) {
         TailArgs a;
         a.base = p.base;
+        a.taps = c->d_taps;
         for (int o = 0; o < p.n_oct; ++o) {
             a.oct_off[o] = p.oct_off[o];
             a.h[o] = p.h[o]; a.w[o] = p.w[o]; a.pitch[o] = p.pitch[o];

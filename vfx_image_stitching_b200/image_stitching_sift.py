@@ -9,6 +9,7 @@ detected once (the reference recomputes each interior image twice), adjacent pai
 the device-resident descriptors.
 """
 import ctypes as C
+import math
 
 import numpy as np
 
@@ -49,10 +50,52 @@ def _as_u8(desc):
     return np.ascontiguousarray(d)
 
 
+def _int_thresh(desc_thresh):
+    """The reference compares an integer-valued distance with `desc_thresh` (strict <, :74): for any
+    real threshold t that is d < ceil(t)."""
+    return int(min(max(math.ceil(desc_thresh), -(2 ** 31) + 1), 2 ** 31 - 1))
+
+
+def ratio_test_matches(descA, descB, ratio=0.7, ctx=None, return_distances=False):
+    """The good-match filter of sift_visualizeUI.py:247-257 (knnMatch(k=2), m.distance < 0.7 * n.distance)
+    with EXACT nearest / second-nearest neighbours and exact integer arithmetic: row i of descA is kept iff
+    den^2 * d1 < num^2 * d2 on the squared distances, ratio = num / den (7 / 10 for the reference's 0.7;
+    other ratios are taken as the closest fraction with denominator <= 1000).  The reference asks
+    approximate FLANN KD-trees for the neighbours, so its own list is not reproducible run to run.
+    Returns (ia, ib) int32 -- query rows in order and their nearest train rows -- and, when asked,
+    the squared distances (d1, d2) of every query row."""
+    from fractions import Fraction
+    ctx = ctx or default_context()
+    fr = Fraction(ratio).limit_denominator(1000)
+    if fr <= 0:
+        raise ValueError('ratio must be positive')
+    A = _as_u8(descA)
+    B = _as_u8(descB)
+    ia = np.zeros(len(A), np.int32)
+    ib = np.zeros(len(A), np.int32)
+    d1 = np.full(len(A), np.iinfo(np.int32).max, np.int32)
+    d2 = np.full(len(A), np.iinfo(np.int32).max, np.int32)
+    n = C.c_int32(0)
+    if len(A):
+        check(ctx.lib.b200sift_ratio_match(ctx.handle, ptr(A), len(A), ptr(B) if len(B) else None, len(B), 0,
+                                           fr.numerator, fr.denominator, ptr(ia), ptr(ib), ptr(d1), ptr(d2),
+                                           C.byref(n)))
+    ia, ib = ia[:n.value].copy(), ib[:n.value].copy()
+    return (ia, ib, d1, d2) if return_distances else (ia, ib)
+
+
+def good_matches(descA, descB, ratio=0.7, ctx=None):
+    """ratio_test_matches as the list of cv2.DMatch the GUI draws (sift_visualizeUI.py:254-257):
+    queryIdx / trainIdx / distance = Euclidean distance of the pair."""
+    import cv2
+    ia, ib, d1, _ = ratio_test_matches(descA, descB, ratio, ctx, return_distances=True)
+    return [cv2.DMatch(int(i), int(j), float(np.sqrt(np.float32(d1[i])))) for i, j in zip(ia, ib)]
+
+
 def match_keypoints(kpsA, descA, kpsB, descB, desc_thresh=25000, ctx=None):
     """The match list of image_stitching_sift.py:63-79 -> (ia, ib, [((xA,yA),(xB,yB)), ...])."""
     idx, d2 = match_descriptors(descA, descB, ctx)
-    keep = (d2 < desc_thresh) & (idx != -1)
+    keep = (d2 < _int_thresh(desc_thresh)) & (idx != -1)
     ia = np.nonzero(keep)[0].astype(np.int32)
     ib = idx[keep]
     matches = [(kpsA[i].pt, kpsB[j].pt) for i, j in zip(ia, ib)]
@@ -65,7 +108,7 @@ def ransac(matches, dist_sq_thresh=3, ctx=None):
     if len(matches) == 0:
         return (0, 0), None
     ctx = ctx or default_context()
-    m = np.ascontiguousarray(np.asarray(matches, dtype=np.float64).reshape(-1, 4).astype(np.float32))
+    m = np.ascontiguousarray(np.asarray(matches, dtype=np.float64).reshape(-1, 4))   # Python floats, as :94-96
     mv = (C.c_double * 2)()
     best = C.c_int32()
     check(ctx.lib.b200sift_ransac(ctx.handle, ptr(m), len(m), float(dist_sq_thresh), mv, C.byref(best)))
@@ -134,7 +177,7 @@ def match_pairs(pairs, ransac_thr=3, desc_thresh=25000, ctx=None):
     nm = np.zeros(n, np.int32)
     best = np.zeros(n, np.int32)
     xy = np.zeros((n, 4), np.float32)
-    check(ctx.lib.b200sift_match_pairs(ctx.handle, n, pr.ctypes.data_as(C.POINTER(C.c_int32)), int(desc_thresh),
+    check(ctx.lib.b200sift_match_pairs(ctx.handle, n, pr.ctypes.data_as(C.POINTER(C.c_int32)), _int_thresh(desc_thresh),
                                        float(ransac_thr), sh.ctypes.data_as(C.POINTER(C.c_double)),
                                        nm.ctypes.data_as(C.POINTER(C.c_int32)),
                                        best.ctypes.data_as(C.POINTER(C.c_int32)), ptr(xy)))

@@ -176,12 +176,14 @@ class GpuBackend(BackendBase):
         return hdr, (idx.value if idx.value >= 0 else None)
 
     def match_pairs_into(self, pairs, ransac_thr, desc_thresh, res):
+        from . import image_stitching_sift as iss
         from ._capi import check
         if not pairs:
             return
         pr = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1, 2))
         check(self.ctx.lib.b200sift_match_pairs_device(self.ctx.handle, len(pairs),
-                                                       pr.ctypes.data_as(C.POINTER(C.c_int32)), int(desc_thresh),
+                                                       pr.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                       iss._int_thresh(desc_thresh),
                                                        float(ransac_thr), C.c_void_p(res.data_ptr()),
                                                        res.stride(0) * res.element_size()))
 
@@ -283,7 +285,8 @@ def sharded_panorama_stream(jobs, backends, ransac_thr=3, desc_thresh=25000, dis
     thread; (2) exchange + matching + result all-gather -- every collective is issued from the calling
     thread, in job order, so all ranks issue them in the same order.  Job k uses backends[k % len(backends)]
     (one library context each): while stage 2 of job k runs, stage 1 of the next len(backends) - 1 jobs is
-    already on the GPU with the other contexts.  `after(k, backend, shifts, counts)` (optional) runs in the calling thread after job
+    already on the GPU with the other contexts.  With a single backend there is nothing to overlap with:
+    the two stages of every job run one after the other on the calling thread.  `after(k, backend, shifts, counts)` (optional) runs in the calling thread after job
     k, e.g. to download its results.  Returns [(shifts, counts)] per job -- identical to calling
     sharded_panorama_shifts job by job."""
     from concurrent.futures import ThreadPoolExecutor
@@ -300,7 +303,18 @@ def sharded_panorama_stream(jobs, backends, ransac_thr=3, desc_thresh=25000, dis
         return lo, hi, np.asarray(backends[k % n_be].detect([images[i] for i in range(lo, hi)]), np.int64)
 
     out = []
-    ahead = max(1, n_be - 1)   # stage-1 jobs in flight: job k+j uses backends[(k+j) % n_be], all distinct
+    ahead = n_be - 1   # stage-1 jobs in flight next to stage 2 of job k: backends (k+1..k+ahead) % n_be, all != k % n_be
+    if ahead == 0:     # one context: stage 1 of job k+1 would overwrite what stage 2 of job k still reads
+        for k in range(len(jobs)):
+            lo, hi, counts_local = stage1(k)
+            be = backends[0]
+            with be.stream_ctx(device):
+                res = _exchange_and_match(jobs[k], be, ransac_thr, desc_thresh, dist, device, rank, world, lo, hi,
+                                          len(jobs[k]), counts_local)
+            if after is not None:
+                after(k, be, *res)
+            out.append(res)
+        return out
     with ThreadPoolExecutor(ahead) as pool:
         futs = {k: pool.submit(stage1, k) for k in range(min(ahead, len(jobs)))}
         for k in range(len(jobs)):

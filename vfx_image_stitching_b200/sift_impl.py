@@ -255,24 +255,33 @@ def generate_DoG_images(gaussian_images):
 def find_scale_space_extrema(gaussian_images, dog_images, num_intervals, sigma, border, contrast_threshold=0.04):
     """sift_impl.py:117-140 -> list[cv2.KeyPoint] in the reference's scan order (base-image coordinates).
 
-    `dog_images` is accepted for signature compatibility; the kernels form the DoG as the float32
-    difference of adjacent Gaussian layers, which is exactly what generate_DoG_images returns.
+    Extrema and the quadratic fit read `dog_images` (:124-129), orientations read `gaussian_images`
+    (:135-136), like the reference.  With dog_images=None the DoG is the float32 difference of
+    adjacent Gaussian layers (what generate_DoG_images returns), formed on the fly and never stored.
     """
-    arr = find_scale_space_extrema_array(gaussian_images, num_intervals, sigma, border, contrast_threshold)
+    arr = find_scale_space_extrema_array(gaussian_images, num_intervals, sigma, border, contrast_threshold,
+                                         dog_images=dog_images)
     return array_to_keypoints(arr)
 
 
-def find_scale_space_extrema_array(gaussian_images, num_intervals=3, sigma=1.6, border=5, contrast_threshold=0.04):
+def find_scale_space_extrema_array(gaussian_images, num_intervals=3, sigma=1.6, border=5, contrast_threshold=0.04,
+                                   dog_images=None):
     ctx = default_context()
     flat, h, w, n_oct, n_layers = _as_pyramid(gaussian_images)
+    dflat, dptr = None, None
+    if dog_images is not None:
+        dflat, dh, dw, d_oct, d_layers = _as_pyramid(dog_images)
+        if (dh, dw, d_oct, d_layers) != (h, w, n_oct, n_layers - 1):
+            raise ValueError('dog_images does not match gaussian_images')
+        dptr = ptr_array(dflat)
     p = default_params(sigma=sigma, num_intervals=num_intervals, image_border_width=border,
                        contrast_threshold=contrast_threshold)
     cap = 1 << 15
     while True:
         out = np.zeros(cap, KP_DTYPE)
         n = C.c_int32()
-        rc = ctx.lib.b200sift_find_extrema(ctx.handle, C.byref(p), ptr_array(flat), h, w, n_oct, n_layers, ptr(out),
-                                           cap, C.byref(n))
+        rc = ctx.lib.b200sift_find_extrema(ctx.handle, C.byref(p), ptr_array(flat), dptr, h, w, n_oct, n_layers,
+                                           ptr(out), cap, C.byref(n))
         if rc == -3 and n.value > cap:  # B200SIFT_ECAPACITY: the caller's buffer was too small
             cap = int(n.value)
             continue
@@ -305,6 +314,66 @@ def is_pixel_an_extremum(prev_patch, curr_patch, next_patch, threshold):
         return False
     cube = np.stack([prev_patch, curr_patch, next_patch])
     return bool(np.all(val >= cube)) if val > 0 else bool(np.all(val <= cube))
+
+
+def localize_extrema(cands, layers, num_intervals=3, sigma=1.6, contrast_threshold=0.04, border=5, eigen_ratio=10,
+                     max_iter=5, is_dog=False, octave_base=-1):
+    """Batched localize_extremum_via_quadratic_fit (sift_impl.py:169-211): `cands` = (n, 4) int32 rows
+    (octave, layer, y, x) -- the format extrema_candidates returns; `layers` = a [octave][layer]
+    pyramid of Gaussian layers (is_dog=False) or DoG layers (is_dog=True), or, with octave_base >= 0,
+    the single octave `octave_base` as [[layer, ...]].  Returns (keypoint structured array (n),
+    final_layer int32 (n), -1 where the reference returns None)."""
+    ctx = default_context()
+    cands = np.ascontiguousarray(np.asarray(cands, np.int32).reshape(-1, 4))
+    flat, h, w, n_oct, n_layers = _as_pyramid(layers)
+    p = default_params(sigma=sigma, num_intervals=num_intervals, image_border_width=border,
+                       contrast_threshold=contrast_threshold, eigen_ratio=eigen_ratio, max_iter=max_iter)
+    kps = np.zeros(len(cands), KP_DTYPE)
+    lyr = np.full(len(cands), -1, np.int32)
+    check(ctx.lib.b200sift_localize(ctx.handle, C.byref(p), ptr_array(flat), int(bool(is_dog)), h, w, n_oct, n_layers,
+                                    int(octave_base), ptr(cands), len(cands), ptr(kps), ptr(lyr)))
+    return kps, lyr
+
+
+def localize_extremum_via_quadratic_fit(x, y, layer, octave, num_intervals, dog_octave, sigma, contrast_threshold,
+                                        border, eigen_ratio=10, max_iter=5):
+    """sift_impl.py:169-211 -> (cv2.KeyPoint, final layer) or None.  `dog_octave` = dog_images[octave]
+    (the num_intervals + 2 DoG layers of that octave), exactly what the reference is called with (:128-129)."""
+    kps, lyr = localize_extrema([(octave, layer, y, x)], [list(dog_octave)], num_intervals, sigma, contrast_threshold,
+                                border, eigen_ratio, max_iter, is_dog=True, octave_base=octave)
+    if lyr[0] < 0:
+        return None
+    k = kps[0]
+    kp = _KeyPoint()
+    kp.pt = (float(k['x']), float(k['y']))
+    kp.octave = int(k['octave'])
+    kp.size = float(k['size'])
+    kp.response = float(k['response'])
+    return kp, int(lyr[0])
+
+
+def keypoints_with_orientations(kps, octave, gauss_img, radius_factor=3, num_bins=36, peak_ratio=0.8,
+                                scale_factor=1.5):
+    """Batched compute_keypoints_with_orientations (sift_impl.py:246-293) for a keypoint structured array
+    on one Gaussian image: returns (oriented keypoints (m) in input order / ascending bin, counts (n))."""
+    ctx = default_context()
+    kps = np.ascontiguousarray(kps, KP_DTYPE)
+    img = np.ascontiguousarray(gauss_img, np.float32)
+    p = default_params(radius_factor=radius_factor, ori_bins=num_bins, peak_ratio=peak_ratio, scale_factor=scale_factor)
+    out = np.zeros((len(kps), int(num_bins)), KP_DTYPE)
+    counts = np.zeros(len(kps), np.int32)
+    check(ctx.lib.b200sift_orientations(ctx.handle, C.byref(p), ptr(kps), len(kps), int(octave), ptr(img), img.shape[0],
+                                        img.shape[1], ptr(out), ptr(counts)))
+    flat = np.concatenate([out[i, :counts[i]] for i in range(len(kps))]) if len(kps) else out.reshape(-1)
+    return flat, counts
+
+
+def compute_keypoints_with_orientations(keypoint, octave, gauss_img, radius_factor=3, num_bins=36, peak_ratio=0.8,
+                                        scale_factor=1.5):
+    """sift_impl.py:246-293 -> list[cv2.KeyPoint], one per histogram peak (ascending bin)."""
+    arr = keypoints_to_array([keypoint])
+    out, _ = keypoints_with_orientations(arr, octave, gauss_img, radius_factor, num_bins, peak_ratio, scale_factor)
+    return array_to_keypoints(out)
 
 
 def compute_gradient_at_center_pixel(cube):
@@ -379,15 +448,15 @@ def generate_descriptors(keypoints, gaussian_images, window_width=4, num_bins=8,
     """sift_impl.py:361-526 -> float32 (N,128), integer valued; shape (0,) for an empty list."""
     if len(keypoints) == 0:
         return np.array([], dtype='float32')
-    if window_width != 4 or num_bins != 8:
-        raise NotImplementedError('the descriptor kernel is specialised for the 4x4x8 layout of the reference')
+    if window_width < 1 or num_bins < 1 or window_width * window_width * num_bins > 1024:
+        raise ValueError('window_width**2 * num_bins must be in 1..1024')
     ctx = default_context()
     flat, h, w, n_oct, n_layers = _as_pyramid(gaussian_images)
     arr = keypoints if isinstance(keypoints, np.ndarray) else keypoints_to_array(keypoints)
     arr = np.ascontiguousarray(arr, KP_DTYPE)
     p = default_params(scale_multiplier=scale_multiplier, descriptor_max_value=descriptor_max_value,
-                       num_intervals=n_layers - 3)
-    out = np.empty((len(arr), 128), np.float32)
+                       num_intervals=n_layers - 3, window_width=int(window_width), desc_bins=int(num_bins))
+    out = np.empty((len(arr), window_width * window_width * num_bins), np.float32)
     check(ctx.lib.b200sift_descriptors(ctx.handle, C.byref(p), ptr(arr), len(arr), ptr_array(flat), h, w, n_oct,
                                        n_layers, ptr(out)))
     return out
@@ -396,7 +465,8 @@ def generate_descriptors(keypoints, gaussian_images, window_width=4, num_bins=8,
 __all__ = [
     'float_tolerance', 'compute_keypoints_and_descriptors', 'generate_base_image', 'compute_number_of_octaves',
     'generate_gaussian_kernels', 'generate_gaussian_images', 'generate_DoG_images', 'find_scale_space_extrema',
-    'is_pixel_an_extremum', 'compute_gradient_at_center_pixel', 'compute_hessian_at_center_pixel',
+    'is_pixel_an_extremum', 'localize_extremum_via_quadratic_fit', 'compute_keypoints_with_orientations',
+    'localize_extrema', 'keypoints_with_orientations', 'compute_gradient_at_center_pixel', 'compute_hessian_at_center_pixel',
     'compare_keypoints', 'remove_duplicate_keypoints', 'convert_keypoints_to_input_image_size', 'unpack_octave',
     'generate_descriptors', 'detect_and_describe_batch', 'gaussian_blur', 'extrema_candidates', 'stage_stats',
     'keypoints_to_array', 'array_to_keypoints', 'B200SiftError',
