@@ -12,6 +12,7 @@ GOLDEN = os.path.join(ROOT, 'tests', 'golden')
 
 def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a B200 (sm_100a) GPU; run with -m gpu on the GPU box')
+    config.addinivalue_line('markers', 'slow: about a minute of CPU oracle time next to the GPU run')
 
 
 def _has_gpu():
