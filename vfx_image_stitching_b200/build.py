@@ -43,6 +43,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     cc = nvcc()
+    extra_all = os.environ.get('B200SIFT_NVCC_FLAGS', '').split()   # build-time experiments (-D...)
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(('.cuh', '.h'))]
     hdrs.append(os.path.join(HERE, '..', 'include', 'b200sift.h'))
     objs = []
@@ -54,7 +55,7 @@ def build(force=False, verbose=False):
         o = os.path.join(CSRC, src[:-3] + '.o')
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [cc] + ARCH + COMMON + extra + ['-c', s, '-o', o]
+            cmd = [cc] + ARCH + COMMON + extra + extra_all + ['-c', s, '-o', o]
             if verbose:
                 cmd.insert(1, '-Xptxas=-v')
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -21,7 +21,6 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
-enum { CNT_CAND = 0, CNT_LOC = 1, CNT_RAW = 2, CNT_OUT = 3, CNT_HDR = 8, CNT_PER_IMG = 4 };
 
 namespace {
 struct TlMark {
@@ -251,7 +250,7 @@ void b200sift_destroy(b200sift_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     void *ptrs[] = {c->pyr.base, c->d_up, c->d_in, c->d_dog, c->d_cand, c->d_loc, c->d_raw, c->d_raw_desc,
-                    c->d_sort_idx, c->d_keep, c->d_pos, c->d_cub_tmp, c->d_kps, c->d_desc, c->d_counters,
+                    c->d_sort_idx, c->d_keep, c->d_pos, c->d_class_idx, c->d_cub_tmp, c->d_kps, c->d_desc, c->d_counters,
                     c->d_mA, c->d_mB, c->d_mout, c->d_misc, c->d_pair, c->d_tc, c->d_tcsrc, c->d_seg, c->d_ptrs,
                     c->d_taps, c->dog_pyr.base};
     if (c->h_ptrs) cudaFreeHost(c->h_ptrs);
@@ -387,7 +386,7 @@ int b200sift_detect_describe(b200sift_ctx *c, const b200sift_params *params, int
     fill_stats(c);
     const int n_raw = c->h_counters[CNT_RAW];
     B200_CHECK(run_sort_async(c, n_raw, n_images, 0, 1));         // side stream, overlaps the descriptors
-    B200_CHECK(run_describe(c, P, c->d_raw, n_raw, 0, c->d_raw_desc));
+    B200_CHECK(run_describe(c, P, c->d_raw, n_raw, 0, c->d_raw_desc, 1));
     tl_mark(c->stream, "main  describe");
     tr.mark(c, "describe (|| sort)");
     B200_CHECK(run_gather(c, n_raw, n_images, 1, 1, 1));
@@ -1053,7 +1052,7 @@ int b200sift_descriptors(b200sift_ctx *c, const b200sift_params *params, const b
         d_out = (uint8_t *)c->d_misc;
     }
     B200_CUDA(cudaMemcpyAsync(c->d_raw, raw.data(), sizeof(RawKeypoint) * n, cudaMemcpyHostToDevice, c->stream));
-    B200_CHECK(run_describe(c, P, c->d_raw, n, /*converted=*/1, d_out));
+    B200_CHECK(run_describe(c, P, c->d_raw, n, /*converted=*/1, d_out, 0));
     std::vector<uint8_t> u8((size_t)n * dlen);
     B200_CUDA(cudaMemcpyAsync(u8.data(), d_out, u8.size(), cudaMemcpyDeviceToHost, c->stream));
     B200_CUDA(cudaStreamSynchronize(c->stream));

@@ -39,6 +39,19 @@ void tl_report();
         }                                                                \
     } while (0)
 
+// device counters (b200sift_ctx::d_counters): stage totals, the work queues of the warp-per-item
+// kernels, the sizes of the descriptor work classes, then CNT_PER_IMG counters per image
+// (candidates, localized, oriented, output)
+enum {
+    CNT_CAND = 0, CNT_LOC = 1, CNT_RAW = 2, CNT_OUT = 3, CNT_WORK_DESC = 4, CNT_WORK_ORI = 5,
+    CNT_CLASS = 8,   // kDescClasses entries
+    CNT_HDR = 16, CNT_PER_IMG = 4
+};
+// Oriented keypoints are binned by descriptor window size when they are emitted, largest class
+// first in the descriptor kernel's work queue: the windows differ 6x in area, and a large one picked
+// up last would leave its warp running alone (ncu, round 2: SMs idle for a quarter of the kernel).
+constexpr int kDescClasses = 5;
+
 constexpr int kMaxOctaves = 24;
 constexpr int kMaxLayers = 10;  // num_intervals + 3 <= 10
 constexpr int kMaxBlurRadius = 64;
@@ -153,6 +166,7 @@ struct b200sift_ctx {
     b200::Localized *d_loc = nullptr;  int loc_cap = 0;
     b200::RawKeypoint *d_raw = nullptr; int raw_cap = 0;
     uint8_t *d_raw_desc = nullptr;                 // [raw_cap][128]
+    int32_t *d_class_idx = nullptr;                // [kDescClasses][raw_cap] raw indices per work class
     uint32_t *d_sort_idx = nullptr; uint32_t *d_keep = nullptr; uint32_t *d_pos = nullptr;
     void *d_cub_tmp = nullptr; size_t cub_tmp_cap = 0;
     int *d_seg = nullptr; size_t seg_cap = 0; std::vector<int> h_seg;   // per-image segments of the sort
@@ -227,7 +241,7 @@ int run_localize_direct(b200sift_ctx *c, const b200sift_params &p, int use_dog, 
 int run_orient_direct(b200sift_ctx *c, const b200sift_params &p, const b200sift_keypoint *h_kps, int n, int octave,
                       b200sift_keypoint *h_out, int32_t *h_counts);
 int run_describe(b200sift_ctx *c, const b200sift_params &p, const RawKeypoint *d_raw, int n, int converted,
-                 uint8_t *d_out);
+                 uint8_t *d_out, int use_classes);
 int run_sort_gather(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int dedupe, int convert, int with_desc);
 int run_sort_async(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int dedupe);   // on the side stream
 int run_gather(b200sift_ctx *c, int n_raw, int n_img, int dedupe, int convert, int with_desc);

@@ -1,190 +1,330 @@
 // 4x4x8 SIFT descriptors, one warp per oriented keypoint (included by detect.cu, which is
-// compiled with --fmad=false).
+// compiled with --fmad=false; fused multiply-adds below are explicit).
 //
 // Replaces /root/reference/sift_impl.py:349-358 (unpack_octave) and :361-526
 // (generate_descriptors: window gather, trilinear scatter with np.add.at, threshold /
 // normalise / quantise).
 //
-// Two phases per 32 window pixels:
-//   filter  : every lane tests one pixel of the clipped (2*half_w+1)^2 window against the rotated
-//             4x4 grid (|r_rot|, |c_rot| < 2.5*hist_width, float32 with a safety margin -- half
-//             of the window fails, :429-430) and the survivors are compacted into a per-warp
-//             queue with a ballot;
-//   scatter : whenever 32 survivors are queued all lanes evaluate one each, with the reference's
-//             dtypes (float64 geometry :421-426, float32 gradient / orientation :414-417,:455-456),
-//             and add their 8 trilinear shares to a lane-private float32 4x4x8 histogram in
-//             shared memory ([bin][lane]: conflict free, no atomics).  Only the inner 4x4 cells
-//             of the reference's 6x6 tensor are ever read (:509), so shares of the border ring
-//             are dropped.
-// The 32 private histograms are then summed in a fixed order (deterministic), followed by the
-// 0.2 clip, renormalisation and round(512 v) of :512-524 with warp shuffles.
+// The round-1 kernel (tools/experiments/describe_v1.cuh) spent ~300 thread instructions per
+// accumulated window pixel (ncu: 471 M warp instructions for 34.4 k keypoints): float64 grid
+// geometry, libdevice atan2f / expf / sqrtf with their slow-path branches, a four-way search
+// that maps a flat survivor index back to its window row, and separate multiply / add in the
+// histogram update.  This version does the same job in ~half the instructions:
+//   * enumeration.  For a fixed window row the pixels inside the rotated 4x4 grid (:429-430) form
+//     an INTERVAL of x; a lane derives the interval of its row analytically (32 rows = one band).
+//     Intervals are cut into chunks of 8 pixels and a table of 16-bit entries (first x, row, pixel
+//     count of the chunk; 544 B of shared memory) is filled by the row owners; an iteration then
+//     takes 4U consecutive chunks: lane = (chunk slot, pixel of the chunk), ONE 16-bit load gives it
+//     its row and x -- no search, no per-pixel test of the other half of the window, and lanes of a
+//     quarter warp read 8 adjacent pixels (one 32 B sector per gathered row);
+//   * arithmetic in float32 throughout the per-pixel part.  The reference computes the grid
+//     coordinates and the Gaussian weight in float64 (:421-449) and the orientation in float32; the
+//     trilinear split is continuous in all of them, so float32 rounding (1e-7 relative) moves a
+//     histogram bin by parts in 1e7 -- two orders below what flips round(512 v) -- and the parity
+//     tests hold this kernel to the same bars as before (|diff| <= 1 step, >= 97 % of rows identical
+//     to the oracle on the same pyramid, RMS relative L2 < 1e-3 end to end);
+//   * atan2 in degrees as one branch-free minimax polynomial (8 terms, <= 7e-6 deg, below the 3e-5
+//     deg float32 spacing of an angle near 360), MUFU approximations for sqrt / exp2 / reciprocal;
+//   * every histogram update is one FFMA between a shared-memory load and store.
+// Each lane adds its shares to a lane-private float32 4x4x8 histogram in shared memory
+// ([bin][lane]: conflict free, no atomics); only the inner 4x4 cells of the reference's 6x6 tensor
+// are ever read (:509), so shares of the border ring are dropped.  The 32 private histograms are
+// summed in a fixed order (deterministic), followed by the 0.2 clip, renormalisation and
+// round(512 v) of :512-524 with warp shuffles.
 #pragma once
 
-constexpr int kDescWarps = 1;   // one warp per CTA: 13 CTAs (16.4 KB histogram + queue + 1 KB reserve each) fit an SM
+constexpr int kDescWarps = 1;   // one warp per CTA: 13 CTAs (16.4 KB histogram + table + 1 KB reserve each) fit an SM
 constexpr int kDescHistFloats = 128 * 32;
-constexpr int kDescU = 2;                       // surviving pixels evaluated per lane and batch
-constexpr int kDescQueue = 32 * kDescU + 32 + 4;   // also the row table of the interval path (<= 96 rows + sentinel)
-constexpr int kDescMaxRows = 95;   // + 5 sentinel entries
-constexpr size_t kDescSmemPerWarp = kDescHistFloats * sizeof(float) + kDescQueue * sizeof(int);
+#ifndef B200SIFT_DESC_U
+#define B200SIFT_DESC_U 2
+#endif
+constexpr int kDescU = B200SIFT_DESC_U;   // chunk slots per lane and iteration (independent dependency chains)
+constexpr int kDescTab = 544;             // chunk table of one band of rows (bytes, 16-bit entries)
+constexpr int kDescMaxRowLen = 128;       // rows of up to 64 px: bands of 32 rows (<= 256 chunks); up to 128 px: bands of
+                                          // 16 rows (<= 256 chunks); longer rows (huge keypoints of the quirk): plain path
+constexpr size_t kDescSmemPerWarp = kDescHistFloats * sizeof(float) + kDescTab;
+
+__device__ __forceinline__ float fast_rcp(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_sqrt(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_ex2(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// atan2(y, x) mod 2 pi in units of ORIENTATION BINS (2 pi = 8 bins; sift_impl.py:416-417 followed by
+// the bins_per_degree scale of :454-455) without branches: atan(t) on [0, 1] as t * P(t^2) (minimax,
+// max error 2.1e-6 deg, 9e-6 deg evaluated in float32 -- below the 3e-5 deg float32 spacing of an
+// angle near 360), then the octant folds.
+__device__ __forceinline__ float atan2_bins_fast(float y, float x)
+{
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float t = mn * fast_rcp(fmaxf(mx, 1e-30f));   // 0 when both are 0, like atan2(0, 0)
+    const float s = t * t;
+    float p = -5.162433314e-03f;
+    p = __fmaf_rn(p, s, 2.783677512e-02f);
+    p = __fmaf_rn(p, s, -7.118977452e-02f);
+    p = __fmaf_rn(p, s, 1.227682611e-01f);
+    p = __fmaf_rn(p, s, -1.770901683e-01f);
+    p = __fmaf_rn(p, s, 2.539675610e-01f);
+    p = __fmaf_rn(p, s, -4.243689677e-01f);
+    p = __fmaf_rn(p, s, 1.273238699e+00f);
+    float r = p * t;
+    r = ay > ax ? 2.f - r : r;
+    r = x < 0.f ? 4.f - r : r;
+    r = y < 0.f ? 8.f - r : r;
+    return r;
+}
+
+struct DescGeom {
+    float cos_f, sin_f, inv_hw, angle_bins;
+};
+
+// floor(x) for |x| < 2^22 without the conversion pipe: round-to-nearest of x - 0.5 through the
+// 1.5 * 2^23 trick.  At an exact integer it may return x - 1 instead of x; the callers below use
+// floor and the fraction x - floor together in a trilinear split, which is the same for both
+// (weight 0 on the extra cell).  `xm` = x - 0.5 is supplied by the caller (folded into an earlier add).
+constexpr float kMagic = 12582912.f;   // 1.5 * 2^23
+__device__ __forceinline__ int floor_magic(float xm, float &fl)
+{
+    const float t = xm + kMagic;
+    fl = t - kMagic;
+    return __float_as_int(t) - 0x4B400000;
+}
+
+// U window pixels of this lane (offsets fx, fy from the keypoint, the four gradient neighbours g):
+// grid coordinates, weight, orientation bin, trilinear split (:421-500) and the 8 histogram updates
+// of each.  Straight-line code: the U dependency chains interleave; the updates of one pixel are
+// applied before those of the next, which may hit the same bins.
+template <int U>
+__device__ __forceinline__ void desc_eval(float *__restrict__ hl, const float (&fx)[U], const float (&fy)[U],
+                                          const bool (&live)[U], const float (&g)[U][4], const DescGeom &G)
+{
+    constexpr float kExp = -0.125f * 1.4426950408889634f;   // weight_mul (:447) * log2(e)
+    int a0[U], a1[U];
+    float v[U][4], w0[U], w1[U];
+    bool p[U][4];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const float r_rot = __fmaf_rn(fx[u], G.sin_f, fy[u] * G.cos_f);      // :421-422
+        const float c_rot = __fmaf_rn(fx[u], G.cos_f, -(fy[u] * G.sin_f));
+        const float qr = r_rot * G.inv_hw, qc = c_rot * G.inv_hw;
+        // r_bin = qr + 1.5 (:425); -1 < r_bin < 4 (:429-430)  <=>  |qr| < 2.5
+        const bool in = live[u] && fabsf(qr) < 2.5f && fabsf(qc) < 2.5f;
+        float r0f, c0f, o0f;
+        const int r0 = floor_magic(qr + 1.f, r0f), c0 = floor_magic(qc + 1.f, c0f);
+        const float rf = (qr + 1.5f) - r0f, cf = (qc + 1.5f) - c0f;
+        const float gx = g[u][0] - g[u][1];
+        const float gy = g[u][2] - g[u][3];
+        const float mag = fast_sqrt(__fmaf_rn(gx, gx, gy * gy));
+        const float wm = fast_ex2(kExp * __fmaf_rn(qr, qr, qc * qc)) * mag;  // :448-451
+        float ob = atan2_bins_fast(gy, gx) - G.angle_bins;                   // np.mod(ob, 8) in float32 (:455-456):
+        ob = ob >= 8.f ? ob - 8.f : ob;                                      //   |ob| <= 8 here
+        ob = ob < 0.f ? ob + 8.f : ob;                                       //   may round up to 8.0, as numpy's does
+        const int o0 = floor_magic(ob - 0.5f, o0f) & 7;                      // :461-462
+        const float of = ob - (float)o0;                                     // :465 (8.0 - 0 in the rounded-up case)
+        const float c1 = wm * rf, c0w = wm - c1, omcf = 1.f - cf;            // :469-476
+        v[u][0] = c0w * omcf;   // (r0,   c0)
+        v[u][1] = c0w * cf;     // (r0,   c0+1)
+        v[u][2] = c1 * omcf;    // (r0+1, c0)
+        v[u][3] = c1 * cf;      // (r0+1, c0+1)
+        w1[u] = of;
+        w0[u] = 1.f - of;
+        const int cell8 = (r0 * 4 + c0) * 8;
+        a0[u] = (cell8 + o0) * 32;
+        a1[u] = (cell8 + ((o0 + 1) & 7)) * 32;
+        // inner cells only: tensor index r0+dr+1 in [1,4]  <=>  r0+dr in [0,3]; `in` bounds r0, c0 to [-1, 3]
+        const bool pr0 = in && r0 >= 0, pr1 = in && r0 <= 2, pc0 = c0 >= 0, pc1 = c0 <= 2;
+        p[u][0] = pr0 && pc0; p[u][1] = pr0 && pc1; p[u][2] = pr1 && pc0; p[u][3] = pr1 && pc1;
+    }
+    constexpr int koff[4] = {0, 8 * 32, 4 * 8 * 32, 5 * 8 * 32};
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        float h0[4], h1[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // the eight bins of one pixel are distinct: all loads before the first store
+            h0[k] = p[u][k] ? hl[a0[u] + koff[k]] : 0.f;
+            h1[k] = p[u][k] ? hl[a1[u] + koff[k]] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (p[u][k]) {
+                hl[a0[u] + koff[k]] = __fmaf_rn(v[u][k], w0[u], h0[k]);
+                hl[a1[u] + koff[k]] = __fmaf_rn(v[u][k], w1[u], h1[k]);
+            }
+        }
+    }
+}
+
+// One keypoint's window on its pyramid layer (unpack_octave :349-358 and :373-388).
+struct DescWin {
+    const float *img;   // layer (octave + 1, layer) of the keypoint's image; nullptr: nothing to accumulate
+    int pitch, rows, cols, ptx, pty, half_w;
+    float hist_width, angle;
+};
+
+__device__ __forceinline__ DescWin desc_window(const PyrView &v, const DetectParams &dp, const RawKeypoint &K,
+                                               int converted)
+{
+    // convert_keypoints_to_input_image_size (:333-343) unless already done
+    const float kx = converted ? K.x : K.x * 0.5f, ky = converted ? K.y : K.y * 0.5f;
+    const float ksize = converted ? K.size : K.size * 0.5f;
+    const int koct = converted ? K.octave_packed : ((K.octave_packed & ~255) | ((K.octave_packed - 1) & 255));
+    int octv = koct & 255;
+    const int lyr = (koct >> 8) & 255;
+    if (octv >= 128) octv |= -128;
+    const float scl = octv >= 0 ? 1.f / (float)(1 << octv) : (float)(1 << -octv);
+    const int po = octv + 1;
+    const bool ok = (po >= 0 && po < v.n_oct && lyr < v.n_layers);
+    DescWin W;
+    W.rows = ok ? v.h[po] : 1;
+    W.cols = ok ? v.w[po] : 1;
+    W.pitch = ok ? v.pitch[po] : 1;
+    W.img = ok ? v.layer(po, lyr, K.img) : nullptr;
+    // per-keypoint scalars keep the reference's dtypes (:374-388)
+    W.ptx = (int)rint((double)scl * (double)kx);
+    W.pty = (int)rint((double)scl * (double)ky);
+    W.hist_width = (float)dp.scale_multiplier_half * scl * ksize;
+    int half_w = (int)rint((double)W.hist_width * 1.4142135623730951 * 5 * 0.5);
+    const int diag = (int)sqrt((double)((long long)W.rows * W.rows + (long long)W.cols * W.cols));
+    W.half_w = min(half_w, diag);
+    W.angle = K.angle;
+    return W;
+}
+
+// The gathers of a keypoint's window mostly miss L2 (the three layers the keypoints live on are
+// larger than L2 and were last touched several kernels ago): while one keypoint is evaluated the
+// warp asks for the 128 B lines of its NEXT keypoint's window, so that those gathers find L2.
+__device__ __forceinline__ void desc_prefetch(const DescWin &W, int lane)
+{
+    if (!W.img) return;
+    const int rlo = max(W.pty - W.half_w, 1) - 1, rhi = min(W.pty + W.half_w, W.rows - 2) + 1;
+    const int clo = max(W.ptx - W.half_w, 1) - 1, chi = min(W.ptx + W.half_w, W.cols - 2) + 1;
+    if (rhi < rlo || chi < clo) return;
+    const uintptr_t row0 = reinterpret_cast<uintptr_t>(W.img + (size_t)rlo * W.pitch);
+    const uintptr_t first = (row0 + (uintptr_t)clo * 4) & ~(uintptr_t)127;
+    const int lpr = (int)(((row0 + (uintptr_t)chi * 4) >> 7) - (first >> 7)) + 2;   // lines per row (rows shift by pitch)
+    const int n_rows = min(rhi - rlo + 1, 128);
+    for (int r = lane; r < n_rows; r += 32) {
+        uintptr_t a = (first + (uintptr_t)r * W.pitch * 4) & ~(uintptr_t)127;
+        for (int l = 0; l < lpr && l < 6; ++l, a += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    }
+}
 
 __global__ void __launch_bounds__(kDescWarps * 32, 13)
 describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw, int n, int converted,
-                uint8_t *__restrict__ desc_out, int32_t *__restrict__ work_counter)
+                uint8_t *__restrict__ desc_out, int32_t *__restrict__ counters, const int32_t *__restrict__ class_idx,
+                int class_stride)
 {
     extern __shared__ __align__(16) unsigned char dsm[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float *hist = reinterpret_cast<float *>(dsm + (size_t)wib * kDescSmemPerWarp);
-    // queue of surviving window offsets, packed (ys << 16) | (xs & 0xffff): |xs|, |ys| < 32768 because the
-    // window is clipped to the image and pyramid dimensions are below 32768
-    int *q = reinterpret_cast<int *>(hist + kDescHistFloats);
-    auto qx_of = [](int v) { return (v << 16) >> 16; };
-    auto qy_of = [](int v) { return v >> 16; };
-    const int warps_total = gridDim.x * kDescWarps;
+    unsigned short *tab = reinterpret_cast<unsigned short *>(hist + kDescHistFloats);
+    float *hl = hist + lane;
     constexpr int U = kDescU;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    (void)warps_total;
+    const int slot = lane >> 3, pix = lane & 7;
     // keypoint windows differ 6x in size: warps take the next keypoint from a global counter
     // instead of a static stride, which removes the tail where a few warps still work
-    for (;;) {
-        int ki = 0;
-        if (lane == 0) ki = atomicAdd(work_counter, 1);
-        ki = __shfl_sync(0xffffffffu, ki, 0);
-        if (ki >= n) break;
-        const RawKeypoint K = raw[ki];
-        // convert_keypoints_to_input_image_size (:333-343) unless already done
-        const float kx = converted ? K.x : K.x * 0.5f, ky = converted ? K.y : K.y * 0.5f;
-        const float ksize = converted ? K.size : K.size * 0.5f;
-        const int koct = converted ? K.octave_packed : ((K.octave_packed & ~255) | ((K.octave_packed - 1) & 255));
-        // unpack_octave (:349-358)
-        int octv = koct & 255;
-        const int lyr = (koct >> 8) & 255;
-        if (octv >= 128) octv |= -128;
-        const float scl = octv >= 0 ? 1.f / (float)(1 << octv) : (float)(1 << -octv);
-        const int po = octv + 1;
-        const bool ok = (po >= 0 && po < v.n_oct && lyr < v.n_layers);
-        const int rows = ok ? v.h[po] : 1, cols = ok ? v.w[po] : 1, pitch = ok ? v.pitch[po] : 1;
-        const float *img = ok ? v.layer(po, lyr, K.img) : nullptr;
-        const int ptx = (int)rint((double)scl * (double)kx);
-        const int pty = (int)rint((double)scl * (double)ky);
-        const double angle = 360. - (double)K.angle;
+    // Queue position t -> keypoint: with work classes (orient_kernel filled class_idx, largest windows
+    // in class 0) the classes are walked in order, so the small keypoints come last; n is then the sum
+    // of the class sizes.  Without them the raw list is taken as it is.
+    int cls_end[kDescClasses];
+    {
+        int acc = 0;
+#pragma unroll
+        for (int k = 0; k < kDescClasses; ++k) {
+            acc += class_idx ? counters[CNT_CLASS + k] : 0;
+            cls_end[k] = acc;
+        }
+    }
+    auto next_item = [&]() -> int {
+        int t = 0;
+        if (lane == 0) {
+            t = atomicAdd(&counters[CNT_WORK_DESC], 1);
+            if (class_idx && t < n) {
+                int k = 0, start = 0;
+#pragma unroll
+                for (int q = 0; q < kDescClasses - 1; ++q)
+                    if (t >= cls_end[q]) { k = q + 1; start = cls_end[q]; }
+                t = t < cls_end[kDescClasses - 1] ? class_idx[(size_t)k * class_stride + (t - start)] : n;
+            }
+        }
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    int ki = next_item();
+    DescWin W;
+    if (ki < n) W = desc_window(v, dp, raw[ki], converted);
+    while (ki < n) {
+        const int ki_next = next_item();
+        DescWin Wn;
+        if (ki_next < n) {
+            Wn = desc_window(v, dp, raw[ki_next], converted);
+            desc_prefetch(Wn, lane);
+        }
+        const bool ok = W.img != nullptr;
+        const int rows = W.rows, cols = W.cols, pitch = W.pitch, ptx = W.ptx, pty = W.pty, half_w = W.half_w;
+        const float *img = W.img;
+        const float hist_width = W.hist_width;
+        const double angle = 360. - (double)W.angle;
         const double rad = angle * (3.14159265358979323846 / 180.0);
-        const double cos_a = cos(rad), sin_a = sin(rad);
-        const float hist_width = (float)dp.scale_multiplier_half * scl * ksize;
-        int half_w = (int)rint((double)hist_width * 1.4142135623730951 * 5 * 0.5);
-        const int diag = (int)sqrt((double)((long long)rows * rows + (long long)cols * cols));
-        half_w = min(half_w, diag);
-        const double hw = (double)hist_width;
-        const float anglef = (float)angle;
-        const float bins_per_deg = (float)(8 / 360.);
-        const float cos_f = (float)cos_a, sin_f = (float)sin_a;
-        const float lim = 2.5f * hist_width * 1.0001f + 1e-3f;  // float32 pre-filter, exact test below
+        DescGeom G;
+        G.cos_f = (float)cos(rad);
+        G.sin_f = (float)sin(rad);
+        G.inv_hw = 1.f / hist_width;
+        G.angle_bins = (float)angle * (float)(8 / 360.);
+        const float cos_f = G.cos_f, sin_f = G.sin_f;
+        const float lim = 2.5f * hist_width * 1.0001f + 1e-3f;  // float32 pre-filter of the enumeration, exact test per pixel
 
+        {
+            float4 *h4 = reinterpret_cast<float4 *>(hist);
 #pragma unroll 8
-        for (int b = 0; b < 128; ++b) hist[b * 32 + lane] = 0.f;
-
-        // Evaluate TWO surviving pixels per lane (window offsets xs, ys) and scatter their shares.
-        // Straight-line code on purpose: the two independent dependency chains (gather, sqrt,
-        // atan2, exp, shared-memory read-modify-write) interleave and hide each other's latency;
-        // with 16 KB of histogram per warp only 12 warps fit on an SM.
-        const double inv_hw = 1.0 / hw;
-        // gather4: the four neighbours of a queued pixel (every queued pixel lies inside the clipped
-        // window, so the address is always valid).  Issued one batch AHEAD of scatter2: the L2
-        // latency of the gather (the shared-memory histograms leave almost no L1) is covered by the
-        // arithmetic of the previous batch instead of stalling the warp.
-        auto gather4 = [&](const int (&xs)[U], const int (&ys)[U], float (&g)[U][4]) {
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const float *p = img + (size_t)(pty + ys[u]) * pitch + (ptx + xs[u]);
-                g[u][0] = __ldg(p + 1);
-                g[u][1] = __ldg(p - 1);
-                g[u][2] = __ldg(p - pitch);
-                g[u][3] = __ldg(p + pitch);
-            }
-        };
-        auto scatter2 = [&](const int (&xs)[U], const int (&ys)[U], const bool (&live)[U], const float (&g)[U][4]) {
-            bool okc[U][4];
-            float *cell[U][4];
-            float mv[U][4], w0[U], w1[U];
-            int o0[U], o1[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const double r_rot = xs[u] * sin_a + ys[u] * cos_a;
-                const double c_rot = xs[u] * cos_a - ys[u] * sin_a;
-                const double qr = r_rot * inv_hw, qc = c_rot * inv_hw;
-                const double r_bin = qr + 1.5, c_bin = qc + 1.5;
-                const bool in = live[u] && (r_bin > -1.0 && r_bin < 4.0 && c_bin > -1.0 && c_bin < 4.0);
-                const float gx = in ? g[u][0] - g[u][1] : 0.f;
-                const float gy = in ? g[u][2] - g[u][3] : 0.f;
-                const float mag = sqrtf(gx * gx + gy * gy);
-                const float orient = mod360f(atan2f(gy, gx) * B200_RAD2DEGF);
-                const float fqr = (float)qr, fqc = (float)qc;
-                const float wm = expf(-0.125f * (fqr * fqr + fqc * fqc)) * mag;
-                float ob = (orient - anglef) * bins_per_deg;  // np.mod(ob, 8) in float32:
-                ob = ob - 8.f * truncf(ob * 0.125f);          // exact fmod for |ob| < 16
-                if (ob != 0.f) { if (ob < 0.f) ob += 8.f; } else ob = 0.f;
-                const int r0 = __double2int_rd(r_bin), c0 = __double2int_rd(c_bin);
-                o0[u] = ((int)floorf(ob)) & 7;
-                o1[u] = (o0[u] + 1) & 7;
-                const float rf = (float)(r_bin - (double)r0), cf = (float)(c_bin - (double)c0);
-                const float of = ob - (float)o0[u];
-                const float c1 = wm * rf, c0w = wm - c1;
-                mv[u][0] = c0w * (1.f - cf);  // (r0,   c0)
-                mv[u][1] = c0w * cf;          // (r0,   c0+1)
-                mv[u][2] = c1 * (1.f - cf);   // (r0+1, c0)
-                mv[u][3] = c1 * cf;           // (r0+1, c0+1)
-                w1[u] = of;
-                w0[u] = 1.f - of;
-                // inner cells only: tensor index r0+dr+1 in [1,4]  <=>  r0+dr in [0,3]
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int rb = r0 + (k >> 1), cb = c0 + (k & 1);
-                    okc[u][k] = in && ((unsigned)rb < 4u) && ((unsigned)cb < 4u);
-                    cell[u][k] = hist + ((rb * 4 + cb) * 8) * 32 + lane;
-                }
-            }
-            // The eight bins of one pixel are distinct: all loads before the first store.  The
-            // second pixel may hit the same bins, so it is applied after the first one's stores.
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                float h0[4], h1[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    h0[k] = okc[u][k] ? cell[u][k][o0[u] * 32] : 0.f;
-                    h1[k] = okc[u][k] ? cell[u][k][o1[u] * 32] : 0.f;
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    if (okc[u][k]) {
-                        cell[u][k][o0[u] * 32] = h0[k] + mv[u][k] * w0[u];
-                        cell[u][k][o1[u] * 32] = h1[k] + mv[u][k] * w1[u];
-                    }
-                }
-            }
-        };
+            for (int b = 0; b < kDescHistFloats / 128; ++b) h4[b * 32 + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
 
         // the window clipped to the pixels that pass the first mask (:400)
         const int rlo = max(pty - half_w, 1), rhi = min(pty + half_w, rows - 2);
         const int clo = max(ptx - half_w, 1), chi = min(ptx + half_w, cols - 2);
         const int nx = chi - clo + 1, ny = rhi - rlo + 1;
-        const int total = (ok && nx > 0 && ny > 0) ? nx * ny : 0;
-        // ---- which window pixels pass the float32 pre-filter (the rotated 4x4 grid, :429-430)?
-        // For a fixed row the filter  |x*sin + y*cos| < lim && |x*cos - y*sin| < lim  holds on an
-        // INTERVAL of x (each term is monotone in x, also after float32 rounding), so the survivors
-        // are enumerated row by row instead of testing every pixel and compacting with ballots: a
-        // lane derives the interval of its rows analytically, widens it by two pixels and shrinks it
-        // with the very predicate the per-pixel test used -- the survivor set and its row-major order
-        // are exactly those of the per-pixel scan (kept below for windows taller than the row table).
+        const int total_px = (ok && nx > 0 && ny > 0) ? nx * ny : 0;
+        // pixel (xs, ys) of the window = center[ys * pitch + xs]; one 32-bit offset per pixel, the row
+        // above / below through a 64-bit pitch held in registers
+        const char *center = reinterpret_cast<const char *>(img + (ptrdiff_t)pty * pitch + ptx);
+        const ptrdiff_t pitch_b = (ptrdiff_t)pitch * 4;
+        auto gather = [&](int xs, int ys, float (&g)[4]) {
+            const char *p = center + (ys * pitch + xs) * 4;
+            g[0] = __ldg(reinterpret_cast<const float *>(p + 4));
+            g[1] = __ldg(reinterpret_cast<const float *>(p - 4));
+            g[2] = __ldg(reinterpret_cast<const float *>(p - pitch_b));
+            g[3] = __ldg(reinterpret_cast<const float *>(p + pitch_b));
+        };
+        // which pixels of a row pass  |x*sin + y*cos| < lim && |x*cos - y*sin| < lim ?  Each term is monotone
+        // in x (also after float32 rounding), so they form an interval: derived analytically, widened by
+        // two pixels and shrunk with the predicate itself.
         auto keep_px = [&](int xs, float fy) -> bool {
             const float fx = (float)xs;
             return (fabsf(fx * sin_f + fy * cos_f) < lim) && (fabsf(fx * cos_f - fy * sin_f) < lim);
         };
-        if (total > 0 && ny <= kDescMaxRows && total < 32768) {
+        if (total_px > 0 && nx <= kDescMaxRowLen) {
             const int xmin = clo - ptx, xmax = chi - ptx;
-            int T = 0;  // survivors so far (warp-uniform)
-            for (int r0 = 0; r0 < ny; r0 += 32) {
-                const int r = r0 + lane;
+            __syncwarp();
+            const int band_rows = nx <= 64 ? 32 : 16;   // <= 8 resp. 16 chunks per row: at most 256 chunks per band
+            for (int band0 = 0; band0 < ny; band0 += band_rows) {
+                // ---- this lane's row of the band: interval [a, a + cnt) of window offsets
+                const int r = band0 + lane;
                 int a = 0, cnt = 0;
-                if (r < ny) {
+                if (r < ny && lane < band_rows) {
                     const float fy = (float)(rlo + r - pty);
                     float xl = (float)xmin, xh = (float)xmax;
                     bool none = false;
@@ -214,143 +354,89 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
                     }
                     cnt = b >= a ? b - a + 1 : 0;
                 }
-                int incl = cnt;
+                const int nch = (cnt + 7) >> 3;
+                int cend = nch;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += t;
+                    const int t = __shfl_up_sync(0xffffffffu, cend, d);
+                    if (lane >= d) cend += t;
                 }
-                if (r < ny) q[r] = ((T + incl - cnt) << 16) | (a & 0xffff);
-                T += __shfl_sync(0xffffffffu, incl, 31);
-            }
-            if (lane < 5) q[ny + lane] = T << 16;  // sentinels: every item index is below them
-            __syncwarp();
-            // items in batches of 32*U, lane <-> item base + lane + 32u (the assignment of the queue path);
-            // the gather of a batch is issued before the previous batch is evaluated
-            int rw[U];
+                const int cstart = cend - nch;
+                const int total = __shfl_sync(0xffffffffu, cend, 31);   // <= 256 chunks
+                // chunk entry: bits 0-7 first x offset + 128 (|x| <= half_w + 1 <= 65 on this path),
+                // bits 8-12 row of the band, bits 13-15 pixels in the chunk - 1
+                for (int k = 0; k < nch; ++k)
+                    tab[cstart + k] = (unsigned short)((a + 8 * k + 128) | (lane << 8) | ((min(cnt - 8 * k, 8) - 1) << 13));
+                __syncwarp();
+                const int ys_band = rlo + band0 - pty;
+                // chunk slot u of an iteration at chunk c0: chunk c0 + 4u + slot, pixel `pix` of it
+                auto lookup = [&](int c0, int (&xs)[U], int (&ys)[U], bool (&live)[U]) {
 #pragma unroll
-            for (int u = 0; u < U; ++u) rw[u] = 0;
-            int px[U], py[U];
-            float pg[U][4];
-            bool plive[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) { px[u] = 0; py[u] = 0; plive[u] = false; }
-            bool pending = false;  // warp-uniform
-            for (int base = 0; base < T; base += 32 * U) {
-                int sx[U], sy[U];
-                bool live[U];
-                float ng[U][4];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int i = base + lane + 32 * u;
-                    live[u] = i < T;
-                    const int it = live[u] ? i : 0;   // dead lanes gather item 0 (valid address) and drop it
-                    int r = live[u] ? rw[u] : 0;
-                    // advance to the row that holds item `it`: starts are non-decreasing (rows without
-                    // survivors have equal starts), so the number of the next four starts that are <= it
-                    // is the number of rows to skip; four independent loads instead of a dependent chain
-                    for (;;) {
-                        const int s1 = q[r + 1] >> 16, s2 = q[r + 2] >> 16, s3 = q[r + 3] >> 16, s4 = q[r + 4] >> 16;
-                        const int adv = (s1 <= it) + (s2 <= it) + (s3 <= it) + (s4 <= it);
-                        r += adv;
-                        if (adv < 4) break;
+                    for (int u = 0; u < U; ++u) {
+                        const int c = c0 + 4 * u + slot;
+                        const bool have = c < total;
+                        const int e = tab[have ? c : 0];            // total > 0 inside the loop
+                        live[u] = have && pix <= (e >> 13);
+                        xs[u] = (e & 255) - 128 + (live[u] ? pix : 0);   // dead lanes gather a valid pixel and drop it
+                        ys[u] = ys_band + ((e >> 8) & 31);
                     }
-                    if (live[u]) rw[u] = r;
-                    const int e = q[r];
-                    sx[u] = ((e << 16) >> 16) + (it - (e >> 16));
-                    sy[u] = rlo + r - pty;
-                }
-                gather4(sx, sy, ng);
-                if (pending) scatter2(px, py, plive, pg);
-                pending = true;
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    px[u] = sx[u]; py[u] = sy[u]; plive[u] = live[u];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) pg[u][k] = ng[u][k];
-                }
-            }
-            if (pending) scatter2(px, py, plive, pg);
-        } else {
-        int yy = lane / max(nx, 1), xx = lane - yy * max(nx, 1);
-        int qn = 0;  // warp-uniform queue length
-        int px[U], py[U];  // batch whose gather is in flight
-        float pg[U][4];
-        bool all_live[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) { px[u] = 0; py[u] = 0; all_live[u] = true; }
-        bool pending = false;  // warp-uniform
-        for (int idx0 = 0; idx0 < total; idx0 += 32) {
-            const int ys = rlo + yy - pty, xs = clo + xx - ptx;
-            xx += 32;
-            while (xx >= nx) { xx -= nx; ++yy; }
-            const float fx = (float)xs, fy = (float)ys;
-            const bool keep = (idx0 + lane < total) && (fabsf(fx * sin_f + fy * cos_f) < lim) &&
-                              (fabsf(fx * cos_f - fy * sin_f) < lim);
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            if (keep) {
-                const int pos = qn + __popc(m & lt_mask);
-                q[pos] = (ys << 16) | (xs & 0xffff);
-            }
-            qn += __popc(m);
-            __syncwarp();
-            if (qn >= 32 * U) {
-                int sx[U], sy[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int e = q[lane + 32 * u];
-                    sx[u] = qx_of(e); sy[u] = qy_of(e);
-                }
-                const int te = q[lane + 32 * U];
-                __syncwarp();
-                qn -= 32 * U;
-                if (lane < qn) q[lane] = te;
+                };
+                int nxs[U], nys[U];
+                bool nlive[U];
                 float ng[U][4];
-                gather4(sx, sy, ng);
-                if (pending) scatter2(px, py, all_live, pg);
-                pending = true;
+                if (total > 0) {
+                    lookup(0, nxs, nys, nlive);
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    px[u] = sx[u]; py[u] = sy[u];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) pg[u][k] = ng[u][k];
+                    for (int u = 0; u < U; ++u) gather(nxs[u], nys[u], ng[u]);
                 }
-                __syncwarp();
-            }
-        }
-        {
-            // drain: gather of the last (partial) batch goes out before the pending one is evaluated
-            int sx[U], sy[U];
-            bool live[U];
-            float ng[U][4];
+                for (int c0 = 0; c0 < total; c0 += 4 * U) {
+                    float fx[U], fy[U], g[U][4];
+                    bool live[U];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                live[u] = lane + 32 * u < qn;
-                // dead lanes gather queue entry 0 (a valid address when qn > 0) and drop the result
-                const int e = qn > 0 ? q[live[u] ? lane + 32 * u : 0] : 0;
-                sx[u] = qx_of(e); sy[u] = qy_of(e);
+                    for (int u = 0; u < U; ++u) {
+                        fx[u] = (float)nxs[u]; fy[u] = (float)nys[u]; live[u] = nlive[u];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) ng[u][k] = 0.f;
+                        for (int k = 0; k < 4; ++k) g[u][k] = ng[u][k];
+                    }
+                    // the gather of the next iteration goes out before this one is evaluated: its L2
+                    // latency is covered by arithmetic instead of stalling the warp
+                    if (c0 + 4 * U < total) {
+                        lookup(c0 + 4 * U, nxs, nys, nlive);
+#pragma unroll
+                        for (int u = 0; u < U; ++u) gather(nxs[u], nys[u], ng[u]);
+                    }
+                    desc_eval<U>(hl, fx, fy, live, g, G);
+                }
+                __syncwarp();   // the table is rewritten by the next band
             }
-            if (qn > 0) gather4(sx, sy, ng);
-            if (pending) scatter2(px, py, all_live, pg);
-            if (qn > 0) scatter2(sx, sy, live, ng);
-        }
+        } else if (total_px > 0) {
+            // plain path (windows wider than the chunk table allows: keypoints of the non-convergence
+            // quirk with a huge size): every pixel of the clipped window, one per lane
+            for (int idx0 = 0; idx0 < total_px; idx0 += 32) {
+                const int idx = idx0 + lane;
+                const bool have = idx < total_px;
+                const int yy = have ? idx / nx : 0, xx = have ? idx - yy * nx : 0;
+                const int xs1 = clo + xx - ptx, ys1 = rlo + yy - pty;
+                float fx[1] = {(float)xs1}, fy[1] = {(float)ys1}, g[1][4];
+                bool live[1] = {have && keep_px(xs1, (float)ys1)};
+                gather(xs1, ys1, g[0]);
+                desc_eval<1>(hl, fx, fy, live, g, G);
+            }
         }
         __syncwarp();
 
+        // fixed-order sum of the 32 private histograms: lane <-> elements lane + 32 q, 16 B loads in a
+        // rotated order (the eight lanes of a quarter warp read eight different bank groups)
         float vq[4];
         double ss = 0.0;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int e = lane + 32 * q;
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // fixed order, 4 chains
+            const float4 *row4 = reinterpret_cast<const float4 *>(hist + (lane + 32 * q) * 32);
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // 4 chains
 #pragma unroll
-            for (int l = 0; l < 32; l += 4) {
-                s0 += hist[e * 32 + ((l + lane) & 31)];
-                s1 += hist[e * 32 + ((l + 1 + lane) & 31)];
-                s2 += hist[e * 32 + ((l + 2 + lane) & 31)];
-                s3 += hist[e * 32 + ((l + 3 + lane) & 31)];
+            for (int j = 0; j < 8; ++j) {
+                const float4 t = row4[(j + lane) & 7];
+                s0 += t.x; s1 += t.y; s2 += t.z; s3 += t.w;
             }
             const float s = (s0 + s1) + (s2 + s3);
             vq[q] = s;
@@ -376,6 +462,8 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
             desc_out[(size_t)ki * 128 + lane + 32 * q] = (uint8_t)t;
         }
         __syncwarp();
+        ki = ki_next;
+        W = Wn;
     }
 }
 
@@ -469,8 +557,8 @@ describe_generic_kernel(PyrView v, DetectParams dp, int d, int nb, const RawKeyp
         for (int e = lane; e < dlen; e += 32) {
             float s = 0.f;
             for (int l = 0; l < 32; ++l) s += ghist[e * 32 + ((l + lane) & 31)];
-            __syncwarp();
-            ghist[e * 32] = s;
+            ghist[e * 32] = s;   // row e is read and rewritten by this lane only (no warp-level sync here:
+                                 // dlen need not be a multiple of 32, so the trip count differs per lane)
             ss += (double)(s * s);
         }
 #pragma unroll

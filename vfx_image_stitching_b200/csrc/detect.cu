@@ -19,8 +19,6 @@
 
 namespace b200 {
 
-// counters layout
-enum { CNT_CAND = 0, CNT_LOC = 1, CNT_RAW = 2, CNT_OUT = 3, CNT_WORK_DESC = 4, CNT_WORK_ORI = 5, CNT_HDR = 8, CNT_PER_IMG = 4 };
 
 PyrView make_view(const Pyramid &p)
 {
@@ -498,7 +496,7 @@ constexpr int kOriMaxBins = 36;
 __global__ void __launch_bounds__(kOriWarps * 32)
 orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int loc_cap,
               RawKeypoint *__restrict__ raw, int raw_cap, int32_t *__restrict__ counters, int direct_n,
-              int32_t *__restrict__ direct_counts)
+              int32_t *__restrict__ direct_counts, int32_t *__restrict__ class_idx)
 {
     // direct_n >= 0: the per-call form of the stage API (compute_keypoints_with_orientations on a
     // caller's keypoints and ONE Gaussian image, held by `v` as octave 0 / layer 0): the peaks of
@@ -635,6 +633,18 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
                         atomicAdd(&counters[CNT_HDR + img * CNT_PER_IMG + 2], __popc(m));
                     }
                     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+                }
+                if (class_idx) {   // work class of the descriptor kernel: by window half-width (sift_impl.py:386-388)
+                    const float hw = (float)dp.scale_multiplier_half * L.size / (float)(1 << o);   // hist_width (:386) in octave pixels
+                    const float half_w = hw * 3.5355339f;
+                    const int cls = half_w >= 40.f ? 0 : half_w >= 32.f ? 1 : half_w >= 26.f ? 2 : half_w >= 21.f ? 3 : 4;
+                    int cb = 0;
+                    if (lane == __ffs(m) - 1) cb = atomicAdd(&counters[CNT_CLASS + cls], __popc(m));
+                    cb = __shfl_sync(0xffffffffu, cb, __ffs(m) - 1);
+                    if (peak) {
+                        const int slot = base + __popc(m & ((1u << lane) - 1u));
+                        if (slot < raw_cap) class_idx[(size_t)cls * raw_cap + cb + __popc(m & ((1u << lane) - 1u))] = slot;
+                    }
                 }
                 if (peak) {
                     const int slot = base + __popc(m & ((1u << lane) - 1u));
@@ -938,6 +948,8 @@ static int ensure_sparse(b200sift_ctx *c, int cand_cap, int loc_cap, int raw_cap
         size_t cap2 = 0;
         if (c->d_raw_desc) { cudaFree(c->d_raw_desc); c->d_raw_desc = nullptr; }
         B200_CHECK(ensure(&c->d_raw_desc, &cap2, (size_t)rc * 128));
+        cap2 = 0; if (c->d_class_idx) { cudaFree(c->d_class_idx); c->d_class_idx = nullptr; }
+        B200_CHECK(ensure(&c->d_class_idx, &cap2, (size_t)rc * kDescClasses));
         cap2 = 0; if (c->d_sort_idx) { cudaFree(c->d_sort_idx); c->d_sort_idx = nullptr; }
         B200_CHECK(ensure(&c->d_sort_idx, &cap2, (size_t)rc));
         cap2 = 0; if (c->d_keep) { cudaFree(c->d_keep); c->d_keep = nullptr; }
@@ -1061,7 +1073,8 @@ int run_detect(b200sift_ctx *c, const b200sift_params &p, int use_dog)
             c->launches++;
             tl_mark(c->stream, "main  refine");
             orient_kernel<<<c->sm_count * 5, kOriWarps * 32, 0, c->stream>>>(v, dp, c->d_loc, c->loc_cap, c->d_raw,
-                                                                             c->raw_cap, c->d_counters, -1, nullptr);
+                                                                             c->raw_cap, c->d_counters, -1, nullptr,
+                                                                             c->d_class_idx);
             c->launches++;
             tl_mark(c->stream, "main  orient");
         }
@@ -1084,7 +1097,7 @@ int run_detect(b200sift_ctx *c, const b200sift_params &p, int use_dog)
 }
 
 int run_describe(b200sift_ctx *c, const b200sift_params &p, const RawKeypoint *d_raw, int n, int converted,
-                 uint8_t *d_out)
+                 uint8_t *d_out, int use_classes)
 {
     if (n <= 0) return 0;
     B200_ARG(p.window_width >= 1 && p.desc_bins >= 1 &&
@@ -1105,8 +1118,8 @@ int run_describe(b200sift_ctx *c, const b200sift_params &p, const RawKeypoint *d
     if (blocks > c->sm_count * g_desc_occ) blocks = c->sm_count * g_desc_occ;
     B200_CHECK(ensure_counters(c, c->pyr.n_img > 0 ? c->pyr.n_img : 1));
     B200_CUDA(cudaMemsetAsync(c->d_counters + CNT_WORK_DESC, 0, sizeof(int32_t), c->stream));
-    describe_kernel<<<blocks, kDescWarps * 32, smem, c->stream>>>(v, dp, d_raw, n, converted, d_out,
-                                                                  c->d_counters + CNT_WORK_DESC);
+    describe_kernel<<<blocks, kDescWarps * 32, smem, c->stream>>>(v, dp, d_raw, n, converted, d_out, c->d_counters,
+                                                                  use_classes ? c->d_class_idx : nullptr, c->raw_cap);
     c->launches++;
     B200_CUDA(cudaGetLastError());
     return 0;
@@ -1400,7 +1413,7 @@ int run_orient_direct(b200sift_ctx *c, const b200sift_params &p, const b200sift_
     int blocks = (n + kOriWarps - 1) / kOriWarps;
     if (blocks > c->sm_count * 5) blocks = c->sm_count * 5;
     orient_kernel<<<blocks, kOriWarps * 32, 0, c->stream>>>(v, dp, c->d_loc, n, c->d_raw, n * nb, c->d_counters, n,
-                                                            d_counts);
+                                                            d_counts, nullptr);
     c->launches++;
     B200_CUDA(cudaGetLastError());
     std::vector<RawKeypoint> hr((size_t)n * nb);
