@@ -16,29 +16,35 @@
 // SBO = 1 KiB between 8-row groups).  Rows are padded with zeros to a multiple of 256 per image;
 // the pre-pass also writes |row|^2 (padding rows get a sentinel that can never win).
 //
-// Kernel (one CTA per 128 A rows x chunk of B tiles, 6 warps, warp-specialised):
-//   warp 0   TMA producer : A tile once, then B tiles through a 3-stage shared-memory ring
+// Kernel (one CTA per 128 A rows x chunk of B tiles, 10 warps, warp-specialised):
+//   warp 0   TMA producer : A tile once, then B tiles (+ their 1 KiB of per-column key constants)
+//                           through a 4-stage shared-memory ring
 //   warp 1   MMA issuer   : one elected thread issues 4 x tcgen05.mma (M128 N256 K32, kind::i8)
 //                           per B tile into one of two 256-column TMEM accumulators and
 //                           tcgen05.commit's the stage / the accumulator to mbarriers
-//   warps 2-5 epilogue    : thread <-> A row (TMEM lane); tcgen05.ld 32 columns at a time and
-//                           keeps the running top-2 of the packed key
+//   warps 2-9 epilogue    : two warps per TMEM lane quarter, each owning 128 of the 256 columns;
+//                           thread <-> A row (TMEM lane).  tcgen05.ld of the next 32 columns is in
+//                           flight while the current 32 are folded into the running minimum of
 //                               key = (|b_j|^2 - 2 a.b_j) * 256 + (j mod 256)
-//                           = one IMAD + integer min/max per element; the min of the packed key
-//                           is the arg-min with the lowest j winning ties, exactly the strict
-//                           "<" of the reference loop.  |a|^2 is added once per row at the end.
+//                           = one IMAD per element + one three-input minimum (VIMNMX3) per two
+//                           elements (nearest) / min + max per element (top-2); the min of the
+//                           packed key is the arg-min with the lowest j winning ties, exactly the
+//                           strict "<" of the reference loop.  |a|^2 is added once per row at the end.
 // The epilogue of tile t overlaps the MMAs of tile t+1 (double-buffered TMEM) and the TMA of
-// tiles t+2.. (ring).  K = 128 is only four MMA K-steps, so the kernel is epilogue-issue bound by
-// design: see DESIGN.md for the roofline arithmetic.
+// tiles t+2.. (ring).  K = 128 is only four MMA K-steps (512 tensor-pipe cycles per tile at the
+// kind::i8 rate), so the epilogue -- 32 768 accumulators per tile -- has to run at about one
+// element per lane-cycle on every scheduler to keep up: see DESIGN.md for the roofline arithmetic.
 #include <limits.h>
 #include <string.h>
 #include "common.cuh"
 
 namespace b200 {
 
-constexpr int kTcM = 128, kTcN = 256, kTcStages = 3;
-constexpr int kTcABytes = kTcM * 128, kTcBBytes = kTcN * 128;
-constexpr int kTcThreads = 192;
+constexpr int kTcM = 128, kTcN = 256, kTcStages = 4;
+constexpr int kTcKeySlots = kTcStages + 2;   // key-constant ring: a slot is reused kTcStages + 2 tiles later (see producer)
+constexpr int kTcABytes = kTcM * 128, kTcBBytes = kTcN * 128, kTcKeyBytes = kTcN * 4;
+constexpr int kTcEpiWarps = 8;
+constexpr int kTcThreads = (2 + kTcEpiWarps) * 32;
 constexpr int kPadSentinel = 0x7FFFFF;  // |row|^2 of a padding row: key = 0x7FFFFF00 + j > every real key
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -128,7 +134,7 @@ struct PackImg { int src_off, n, dst_off; };  // rows: source offset, count, pac
 
 __global__ void __launch_bounds__(256)
 pack_kernel(const uint8_t *__restrict__ src, const PackImg *__restrict__ imgs, uint8_t *__restrict__ packed,
-            int32_t *__restrict__ nrm)
+            int32_t *__restrict__ nrm, int32_t *__restrict__ ckey)
 {
     const PackImg im = imgs[blockIdx.y];
     const int n_pad = (im.n + kTcN - 1) / kTcN * kTcN;
@@ -146,7 +152,11 @@ pack_kernel(const uint8_t *__restrict__ src, const PackImg *__restrict__ imgs, u
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     s += __shfl_xor_sync(0xffffffffu, s, 4);
-    if (kc == 0) nrm[pr] = r < im.n ? (int32_t)s : kPadSentinel;
+    if (kc == 0) {
+        const int32_t nr = r < im.n ? (int32_t)s : kPadSentinel;
+        nrm[pr] = nr;
+        ckey[pr] = nr * 256 + (pr & 255);   // per-column constant of the packed key (images start at multiples of 256)
+    }
 }
 
 // ------------------------------------------------------------------ the matcher
@@ -154,16 +164,18 @@ struct TcPair { int offA, nA, offB, nB; };  // packed row offsets (multiples of 
 
 template <bool kTop2>
 __global__ void __launch_bounds__(kTcThreads, 1)
-match_tc_kernel(const uint8_t *__restrict__ packed, const int32_t *__restrict__ nrm, const TcPair *__restrict__ pairs,
-                int tiles_per_chunk, int n_chunks, int rows_max, int32_t *__restrict__ part)
+match_tc_kernel(const uint8_t *__restrict__ packed, const int32_t *__restrict__ nrm, const int32_t *__restrict__ ckey,
+                const TcPair *__restrict__ pairs, int tiles_per_chunk, int n_chunks, int rows_max,
+                int32_t *__restrict__ part)
 {
     extern __shared__ __align__(1024) uint8_t tsm[];
     uint8_t *a_s = tsm;                                   // 16 KiB
     uint8_t *b_s = tsm + kTcABytes;                       // kTcStages x 32 KiB
-    int32_t *cj_s = reinterpret_cast<int32_t *>(b_s + kTcStages * kTcBBytes);  // [2][256]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(cj_s + 2 * kTcN);
-    uint64_t *full = bars, *empty = bars + kTcStages, *tfull = bars + 2 * kTcStages, *tempty = tfull + 2,
-             *afull = tempty + 2;
+    int32_t *ck_s = reinterpret_cast<int32_t *>(b_s + kTcStages * kTcBBytes);   // [kTcKeySlots][256]
+    int32_t *red_s = ck_s + kTcKeySlots * kTcN;                                  // [128][4]: upper column half's result
+    uint64_t *bars = reinterpret_cast<uint64_t *>(red_s + kTcM * 4);
+    uint64_t *full = bars, *empty = full + kTcStages, *kfull = empty + kTcStages, *tfull = kfull + kTcKeySlots,
+             *tempty = tfull + 2, *afull = tempty + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(afull + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -175,9 +187,8 @@ match_tc_kernel(const uint8_t *__restrict__ packed, const int32_t *__restrict__ 
     const int t_begin = chunk * tiles_per_chunk, t_end = min(n_tiles_b, t_begin + tiles_per_chunk);
     const int n_tiles = t_end - t_begin;
     if (n_tiles <= 0) {  // nothing of B in this chunk: sentinel (uniform over the CTA)
-        if (warp >= 2) {
-            const int q = warp & 3;
-            const int r2 = m0 + q * 32 + lane;
+        if (warp >= 2 && warp < 6) {
+            const int r2 = m0 + (warp & 3) * 32 + lane;
             if (r2 < P.nA) {
                 int32_t *o = part + (((size_t)blockIdx.z * rows_max + r2) * n_chunks + chunk) * 3;
                 o[0] = -1; o[1] = INT_MAX; o[2] = INT_MAX;
@@ -188,11 +199,12 @@ match_tc_kernel(const uint8_t *__restrict__ packed, const int32_t *__restrict__ 
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kTcStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+        for (int s = 0; s < kTcKeySlots; ++s) mbar_init(&kfull[s], 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], kTcEpiWarps); }
         mbar_init(afull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM: both accumulators = all 512 columns
+    if (warp == 1) {  // TMEM: both accumulators = all 512 columns (one CTA per SM)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                      "r"(512)
                      : "memory");
@@ -205,15 +217,23 @@ match_tc_kernel(const uint8_t *__restrict__ packed, const int32_t *__restrict__ 
 
     if (warp == 0) {
         // ===== TMA producer =====
+        // B tile t goes to stage t % kTcStages once the MMAs of tile t - kTcStages have retired.  Its key
+        // constants go to slot t % kTcKeySlots: the previous user of that slot is tile t - kTcStages - 2,
+        // whose epilogue is complete because the MMAs of tile t - kTcStages (just seen retired) could not
+        // start before it handed its TMEM buffer back.
         if (lane == 0) {
             mbar_arrive_expect_tx(afull, kTcABytes);
             tma_bulk_g2s(a_s, packed + (size_t)(P.offA + m0) * 128, kTcABytes, afull);
+            int s = 0, ks = 0;
             for (int t = 0; t < n_tiles; ++t) {
-                const int s = t % kTcStages;
                 mbar_wait(&empty[s], ((t / kTcStages) & 1) ^ 1);
+                const size_t row0 = (size_t)P.offB + (size_t)(t_begin + t) * kTcN;
                 mbar_arrive_expect_tx(&full[s], kTcBBytes);
-                tma_bulk_g2s(b_s + (size_t)s * kTcBBytes, packed + (size_t)(P.offB + (t_begin + t) * kTcN) * 128,
-                             kTcBBytes, &full[s]);
+                tma_bulk_g2s(b_s + (size_t)s * kTcBBytes, packed + row0 * 128, kTcBBytes, &full[s]);
+                mbar_arrive_expect_tx(&kfull[ks], kTcKeyBytes);
+                tma_bulk_g2s(ck_s + ks * kTcN, ckey + row0, kTcKeyBytes, &kfull[ks]);
+                if (++s == kTcStages) s = 0;
+                if (++ks == kTcKeySlots) ks = 0;
             }
         }
     } else if (warp == 1) {
@@ -221,8 +241,9 @@ match_tc_kernel(const uint8_t *__restrict__ packed, const int32_t *__restrict__ 
         if (lane == 0) {
             mbar_wait(afull, 0);
             const uint32_t a_addr = smem_u32(a_s);
+            int s = 0;
             for (int t = 0; t < n_tiles; ++t) {
-                const int s = t % kTcStages, buf = t & 1;
+                const int buf = t & 1;
                 mbar_wait(&tempty[buf], ((t >> 1) & 1) ^ 1);  // epilogue drained this accumulator
                 mbar_wait(&full[s], (t / kTcStages) & 1);     // B tile landed
                 tc_fence_after();
@@ -234,50 +255,48 @@ match_tc_kernel(const uint8_t *__restrict__ packed, const int32_t *__restrict__ 
                               k > 0 ? 1u : 0u);
                 tc_commit(&empty[s]);    // smem stage reusable once these MMAs retire
                 tc_commit(&tfull[buf]);  // accumulator ready
+                if (++s == kTcStages) s = 0;
             }
         }
     } else {
-        // ===== epilogue: thread <-> A row =====
-        const int q = warp & 3;                 // TMEM lane quarter this warp may access
-        const int r = m0 + q * 32 + lane;       // A row of this thread
-        const int et = (warp - 2) * 32 + lane;  // 0..127 among the epilogue threads
+        // ===== epilogue: thread <-> A row, warp <-> 128 of the tile's 256 columns =====
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access (warp index mod 4)
+        const int half = (warp - 2) >> 2;       // column half: warps 2-5 take columns 0-127, warps 6-9 columns 128-255
+        const int row_l = q * 32 + lane;        // row inside the A tile
+        const int r = m0 + row_l;
         int best_d = INT_MAX, best_j = -1, second_d = INT_MAX;
-        const int na = (r < P.nA) ? nrm[P.offA + r] : 0;
+        int ks = 0;
         for (int t = 0; t < n_tiles; ++t) {
             const int buf = t & 1;
-            // per-column constants of this tile: c_j = |b_j|^2 * 256 + (j mod 256)
-            {
-                const int jb = (t_begin + t) * kTcN;
-                int32_t *cj = cj_s + buf * kTcN;
-                const int2 nb = reinterpret_cast<const int2 *>(nrm + P.offB + jb)[et];
-                cj[2 * et] = nb.x * 256 + 2 * et;
-                cj[2 * et + 1] = nb.y * 256 + 2 * et + 1;
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait(&kfull[ks], (t / kTcKeySlots) & 1);   // this tile's key constants c_j = |b_j|^2 * 256 + (j mod 256)
             mbar_wait(&tfull[buf], (t >> 1) & 1);
             tc_fence_after();
             int m1 = INT_MAX, m2 = INT_MAX;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kTcN);
-            const int4 *cj4 = reinterpret_cast<const int4 *>(cj_s + buf * kTcN);
-#pragma unroll 1
-            for (int c0 = 0; c0 < kTcN; c0 += 32) {
-                int32_t acc[32];
-                tc_ld32(taddr + c0, acc);
-                tc_wait_ld();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kTcN + half * 128);
+            const int4 *cj4 = reinterpret_cast<const int4 *>(ck_s + ks * kTcN + half * 128);
+            int32_t acc[2][32];
+            tc_ld32(taddr, acc[0]);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if (i < 3) tc_ld32(taddr + 32 * (i + 1), acc[(i + 1) & 1]);   // in flight during the arithmetic below
 #pragma unroll
                 for (int g = 0; g < 8; ++g) {
-                    const int4 c = cj4[(c0 >> 2) + g];
-                    const int k0 = acc[4 * g] * -512 + c.x, k1 = acc[4 * g + 1] * -512 + c.y;
-                    const int k2 = acc[4 * g + 2] * -512 + c.z, k3 = acc[4 * g + 3] * -512 + c.w;
+                    const int4 c = cj4[i * 8 + g];
+                    const int32_t *a = acc[i & 1] + 4 * g;
+                    const int k0 = a[0] * -512 + c.x, k1 = a[1] * -512 + c.y;
+                    const int k2 = a[2] * -512 + c.z, k3 = a[3] * -512 + c.w;
                     if (kTop2) {
                         m2 = min(m2, max(m1, k0)); m1 = min(m1, k0);
                         m2 = min(m2, max(m1, k1)); m1 = min(m1, k1);
                         m2 = min(m2, max(m1, k2)); m1 = min(m1, k2);
                         m2 = min(m2, max(m1, k3)); m1 = min(m1, k3);
                     } else {
-                        m1 = min(min(m1, k0), min(k1, min(k2, k3)));
+                        m1 = min(m1, min(k0, k1));
+                        m1 = min(m1, min(k2, k3));
                     }
                 }
+                if (i < 3) tc_wait_ld();
             }
             // accumulator drained: hand it back to the MMA warp
             tc_fence_before();
@@ -292,8 +311,23 @@ match_tc_kernel(const uint8_t *__restrict__ packed, const int32_t *__restrict__ 
             } else if (kTop2) {
                 second_d = min(second_d, td);
             }
+            if (++ks == kTcKeySlots) ks = 0;
         }
-        if (r < P.nA) {
+        // the two column halves of a row meet in shared memory; equal distances: the lower j wins
+        if (half == 1) {
+            red_s[row_l * 4] = best_d; red_s[row_l * 4 + 1] = best_j; red_s[row_l * 4 + 2] = second_d;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kTcEpiWarps * 32) : "memory");
+        if (half == 0 && r < P.nA) {
+            const int od = red_s[row_l * 4], oj = red_s[row_l * 4 + 1], os = red_s[row_l * 4 + 2];
+            if (od < best_d || (od == best_d && (unsigned)oj < (unsigned)best_j)) {
+                if (kTop2) second_d = min(best_d, os);
+                best_d = od;
+                best_j = oj;
+            } else if (kTop2) {
+                second_d = min(second_d, od);
+            }
+            const int na = nrm[P.offA + r];
             int32_t *o = part + (((size_t)blockIdx.z * rows_max + r) * n_chunks + chunk) * 3;
             const bool real = best_j >= 0 && best_j < P.nB;  // padding rows of B can only win when nB == 0
             o[0] = real ? best_j : -1;
@@ -309,7 +343,8 @@ match_tc_kernel(const uint8_t *__restrict__ packed, const int32_t *__restrict__ 
     }
 }
 
-constexpr size_t kTcSmemBytes = kTcABytes + (size_t)kTcStages * kTcBBytes + 2 * kTcN * 4 + 16 * 8 + 64;
+constexpr size_t kTcSmemBytes = kTcABytes + (size_t)kTcStages * kTcBBytes + (size_t)kTcKeySlots * kTcKeyBytes +
+                                kTcM * 4 * 4 + (2 * kTcStages + kTcKeySlots + 5) * 8 + 64;
 
 // Function attributes are per DEVICE: called once for every device a context is created on
 // (b200sift_create, under the init lock), never from a launch path.
@@ -347,13 +382,14 @@ int run_match_tc(b200sift_ctx *c, const uint8_t *d_src, int n_imgs, const int *h
         tp[p].offB = imgs[b].dst_off; tp[p].nB = imgs[b].n;
     }
     size_t cap = c->tc_cap;
-    const size_t need = (size_t)total * 128 + (size_t)total * 4 + imgs.size() * sizeof(PackImg) +
+    const size_t need = (size_t)total * 128 + (size_t)total * 8 + imgs.size() * sizeof(PackImg) +
                         tp.size() * sizeof(TcPair) + 1024;
     B200_CHECK(ensure(&c->d_tc, &cap, need));
     c->tc_cap = cap;
     uint8_t *packed = c->d_tc;
     int32_t *nrm = reinterpret_cast<int32_t *>(packed + (size_t)total * 128);
-    PackImg *d_imgs = reinterpret_cast<PackImg *>(nrm + total);
+    int32_t *ckey = nrm + total;   // total is a multiple of 256: 1 KiB aligned like the TMA slices need
+    PackImg *d_imgs = reinterpret_cast<PackImg *>(ckey + total);
     TcPair *d_tp = reinterpret_cast<TcPair *>(d_imgs + imgs.size());
     // the small host tables must outlive the asynchronous copies: keep them in the context
     c->h_tc_tables.resize(imgs.size() * sizeof(PackImg) + tp.size() * sizeof(TcPair));
@@ -363,17 +399,17 @@ int run_match_tc(b200sift_ctx *c, const uint8_t *d_src, int n_imgs, const int *h
                               c->stream));  // d_imgs and d_tp are adjacent
     if (max_pad > 0) {
         dim3 pg((max_pad * 8 + 255) / 256, n_imgs);
-        pack_kernel<<<pg, 256, 0, c->stream>>>(d_src, d_imgs, packed, nrm);
+        pack_kernel<<<pg, 256, 0, c->stream>>>(d_src, d_imgs, packed, nrm, ckey);
         c->launches++;
     }
     c->last_tiles_per_chunk = tiles_per_chunk;
     c->last_n_chunks = n_chunks_out;
     dim3 grid((rows_max + kTcM - 1) / kTcM, n_chunks_out, n_pairs);
     if (top2)
-        match_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, c->stream>>>(packed, nrm, d_tp, tiles_per_chunk,
+        match_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, c->stream>>>(packed, nrm, ckey, d_tp, tiles_per_chunk,
                                                                            n_chunks_out, rows_max, d_part);
     else
-        match_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, c->stream>>>(packed, nrm, d_tp, tiles_per_chunk,
+        match_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, c->stream>>>(packed, nrm, ckey, d_tp, tiles_per_chunk,
                                                                             n_chunks_out, rows_max, d_part);
     c->launches++;
     B200_CUDA(cudaGetLastError());
@@ -422,16 +458,17 @@ int bench_match_tc(b200sift_ctx *c, int nA, int nB, int top2, int iters, float *
     const int padA = (nA + kTcN - 1) / kTcN * kTcN, padB = (nB + kTcN - 1) / kTcN * kTcN;
     uint8_t *packed = c->d_tc;
     int32_t *nrm = reinterpret_cast<int32_t *>(packed + (size_t)(padA + padB) * 128);
-    TcPair *d_tp = reinterpret_cast<TcPair *>(reinterpret_cast<PackImg *>(nrm + padA + padB) + 2);
+    int32_t *ckey = nrm + padA + padB;
+    TcPair *d_tp = reinterpret_cast<TcPair *>(reinterpret_cast<PackImg *>(ckey + padA + padB) + 2);
     dim3 grid((nA + kTcM - 1) / kTcM, n_chunks, 1);
     double acc = 0;
     for (int it = 0; it < iters + 2; ++it) {
         B200_CUDA(cudaEventRecord(c->ev0, c->stream));
         if (top2)
-            match_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, c->stream>>>(packed, nrm, d_tp, tpc, n_chunks, nA,
+            match_tc_kernel<true><<<grid, kTcThreads, kTcSmemBytes, c->stream>>>(packed, nrm, ckey, d_tp, tpc, n_chunks, nA,
                                                                                c->d_mout);
         else
-            match_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, c->stream>>>(packed, nrm, d_tp, tpc, n_chunks, nA,
+            match_tc_kernel<false><<<grid, kTcThreads, kTcSmemBytes, c->stream>>>(packed, nrm, ckey, d_tp, tpc, n_chunks, nA,
                                                                                 c->d_mout);
         B200_CUDA(cudaEventRecord(c->ev1, c->stream));
         B200_CUDA(cudaEventSynchronize(c->ev1));
@@ -445,18 +482,29 @@ int bench_match_tc(b200sift_ctx *c, int nA, int nB, int top2, int iters, float *
     return 0;
 }
 
-// chunking shared by both callers: enough CTAs for ~2 per SM, at least one B tile per chunk
+// Chunking shared by both callers.  One CTA is resident per SM (it owns all 512 TMEM columns), so
+// the launch runs in waves of sm_count CTAs; a CTA costs its B tiles plus a fixed start-up (TMEM
+// allocation, A tile, first B tile, pipeline fill: about two tile times).  The number of B chunks is
+// the one that minimises waves x (tiles per chunk + start-up): small problems are cut until they fill
+// the machine, large ones until the last wave is nearly full (64k x 64k: 512 A tiles x 2 chunks =
+// 6.9 waves instead of 3.5).
 void tc_chunking(const b200sift_ctx *c, int rows_max, int nb_max, int n_pairs, int *tiles_per_chunk, int *n_chunks)
 {
     const int a_tiles = (rows_max + kTcM - 1) / kTcM;
     const int b_tiles = nb_max > 0 ? (nb_max + kTcN - 1) / kTcN : 1;
     const long long ctas_one = (long long)a_tiles * n_pairs;  // with a single chunk
-    int want_chunks = (int)((2LL * c->sm_count + ctas_one - 1) / ctas_one);
-    if (want_chunks < 1) want_chunks = 1;
-    if (want_chunks > b_tiles) want_chunks = b_tiles;
-    int tpc = (b_tiles + want_chunks - 1) / want_chunks;
-    *tiles_per_chunk = tpc;
-    *n_chunks = (b_tiles + tpc - 1) / tpc;
+    long long best_cost = -1;
+    int best_tpc = b_tiles;
+    const int max_chunks = b_tiles < 64 ? b_tiles : 64;
+    for (int ch = 1; ch <= max_chunks; ++ch) {
+        const int tpc = (b_tiles + ch - 1) / ch;
+        const int real_ch = (b_tiles + tpc - 1) / tpc;
+        const long long waves = (ctas_one * real_ch + c->sm_count - 1) / c->sm_count;
+        const long long cost = waves * (tpc + 2);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_tpc = tpc; }
+    }
+    *tiles_per_chunk = best_tpc;
+    *n_chunks = (b_tiles + best_tpc - 1) / best_tpc;
 }
 
 }  // namespace b200
