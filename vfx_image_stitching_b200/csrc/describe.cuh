@@ -36,32 +36,13 @@
 constexpr int kDescWarps = 1;   // one warp per CTA: 13 CTAs (16.4 KB histogram + table + 1 KB reserve each) fit an SM
 constexpr int kDescHistFloats = 128 * 32;
 #ifndef B200SIFT_DESC_U
-#define B200SIFT_DESC_U 2
+#define B200SIFT_DESC_U 3
 #endif
 constexpr int kDescU = B200SIFT_DESC_U;   // chunk slots per lane and iteration (independent dependency chains)
 constexpr int kDescTab = 544;             // chunk table of one band of rows (bytes, 16-bit entries)
 constexpr int kDescMaxRowLen = 128;       // rows of up to 64 px: bands of 32 rows (<= 256 chunks); up to 128 px: bands of
                                           // 16 rows (<= 256 chunks); longer rows (huge keypoints of the quirk): plain path
 constexpr size_t kDescSmemPerWarp = kDescHistFloats * sizeof(float) + kDescTab;
-
-__device__ __forceinline__ float fast_rcp(float x)
-{
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float fast_sqrt(float x)
-{
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float fast_ex2(float x)
-{
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
 
 // atan2(y, x) mod 2 pi in units of ORIENTATION BINS (2 pi = 8 bins; sift_impl.py:416-417 followed by
 // the bins_per_degree scale of :454-455) without branches: atan(t) on [0, 1] as t * P(t^2) (minimax,

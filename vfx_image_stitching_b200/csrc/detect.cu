@@ -19,6 +19,8 @@
 
 namespace b200 {
 
+#include "fastmath.cuh"
+
 
 PyrView make_view(const Pyramid &p)
 {
@@ -511,12 +513,40 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
     const int warps_total = gridDim.x * kOriWarps;
     double(*hist)[32] = hist_s[wib];
     (void)warps_total;
-    for (;;) {  // dynamic work queue: windows are (2r+1)^2 with r = 7..17
-        int li = 0;
-        if (lane == 0) li = atomicAdd(&counters[CNT_WORK_ORI], 1);
-        li = __shfl_sync(0xffffffffu, li, 0);
-        if (li >= n) break;
-        const Localized L = loc[li];
+    // dynamic work queue: windows are (2r+1)^2 with r = 7..17.  The next item is fetched one keypoint
+    // ahead and the 128 B lines of its window are requested into L2 while this one is evaluated (the
+    // layer was last touched by the blur kernels and mostly left L2 since).
+    auto next_item = [&]() -> int {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&counters[CNT_WORK_ORI], 1);
+        return __shfl_sync(0xffffffffu, t, 0);
+    };
+    auto prefetch_window = [&](const Localized &P) {
+        const int po = (P.img_o_l >> 8) & 255, pov = direct ? 0 : po;
+        const int ph = v.h[pov], pw = v.w[pov], pp = v.pitch[pov];
+        const float *pimg = v.layer(pov, direct ? 0 : (int)(P.img_o_l & 255), P.img_o_l >> 16);
+        const float pscale = (float)(dp.scale_factor * (double)P.size) / (float)(1 << (po + 1));
+        const int prad = (int)fminf(rintf(dp.radius_factor_f * pscale), 64.f);
+        const int pcy = (int)rintf(P.y / (float)(1 << po)), pcx = (int)rintf(P.x / (float)(1 << po));
+        const int y0 = max(pcy - prad - 1, 0), y1 = min(pcy + prad + 1, ph - 1);
+        const int x0 = max(pcx - prad - 1, 0), x1 = min(pcx + prad + 1, pw - 1);
+        if (y1 < y0 || x1 < x0) return;
+        for (int yy = y0 + lane; yy <= y1; yy += 32) {
+            const uintptr_t a0 = reinterpret_cast<uintptr_t>(pimg + (size_t)yy * pp + x0) & ~(uintptr_t)127;
+            const uintptr_t a1 = reinterpret_cast<uintptr_t>(pimg + (size_t)yy * pp + x1) & ~(uintptr_t)127;
+            for (uintptr_t a = a0; a <= a1; a += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+        }
+    };
+    int li = next_item();
+    Localized L;
+    if (li < n) L = loc[li];
+    while (li < n) {
+        const int li_next = next_item();
+        Localized Ln;
+        if (li_next < n) {
+            Ln = loc[li_next];
+            prefetch_window(Ln);
+        }
         const int img = L.img_o_l >> 16, o = (L.img_o_l >> 8) & 255, layer = L.img_o_l & 255;
         const int ov = direct ? 0 : o;
         const int h = v.h[ov], w = v.w[ov], pitch = v.pitch[ov];
@@ -524,6 +554,7 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
         const float scale = (float)(dp.scale_factor * (double)L.size) / (float)(1 << (o + 1));
         const int radius = (int)fminf(rintf(dp.radius_factor_f * scale), 1048576.f);
         const float weight_fac = -0.5f / (scale * scale);
+        const float weight_fac2 = weight_fac * 1.4426950408889634f;   // exp(w d) = 2^(w log2(e) d)
         const int cy = (int)rintf(L.y / (float)(1 << o));
         const int cx = (int)rintf(L.x / (float)(1 << o));
         for (int b = 0; b < nb; ++b) hist[b][lane] = 0.0;
@@ -573,10 +604,10 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
                 const int dy = cyv[u] - cy, dx = cxv[u] - cx;
                 const float gx = g[u][0] - g[u][1];
                 const float gy = g[u][2] - g[u][3];
-                const float mag = sqrtf(gx * gx + gy * gy);
-                const float ang = mod360f(atan2f(gy, gx) * B200_RAD2DEGF);
-                const float wgt = expf(weight_fac * (float)(dx * dx + dy * dy));
-                int bi = (int)rintf(ang * (float)nb / 360.f);  // ang in [0, 360): bi in [0, nb]
+                const float mag = fast_sqrt(__fmaf_rn(gx, gx, gy * gy));
+                const float ang = atan2_deg_fast(gy, gx);
+                const float wgt = fast_ex2(weight_fac2 * (float)(dx * dx + dy * dy));
+                int bi = (int)rintf(ang * (float)nb / 360.f);  // ang in [0, 360]: bi in [0, nb]
                 if (bi >= nb) bi -= nb;                         // == bi % nb (:279)
                 bin[u] = live[u] ? bi : -1;
                 val[u] = wgt * mag;
@@ -668,6 +699,8 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
         }
         if (direct && lane == 0) direct_counts[li] = emitted;
         __syncwarp();
+        li = li_next;
+        L = Ln;
     }
 }
 

@@ -390,8 +390,18 @@ static int ring_setup()
     return 0;
 }
 
+// input stages (cp.async batches in flight + 1) per radius; build-time overridable for sweeps
+#ifndef B200SIFT_RING_S_SMALL
+#define B200SIFT_RING_S_SMALL 3
+#endif
+#ifndef B200SIFT_RING_S_10
+#define B200SIFT_RING_S_10 3
+#endif
+#ifndef B200SIFT_RING_S_13
+#define B200SIFT_RING_S_13 2
+#endif
 template <int R>
-struct RingDepth { static constexpr int S = (R >= 12) ? 2 : 3; };
+struct RingDepth { static constexpr int S = (R >= 12) ? B200SIFT_RING_S_13 : (R >= 10) ? B200SIFT_RING_S_10 : B200SIFT_RING_S_SMALL; };
 
 constexpr size_t kTileSmemMax = (size_t)((32 + 2 * kMaxBlurRadius) * (32 + 2 * kMaxBlurRadius) +
                                          (32 + 2 * kMaxBlurRadius) * 32) * sizeof(float);
@@ -449,6 +459,9 @@ static int launch_ring(b200sift_ctx *c, const float *src, float *dst, float *dst
         seg = ((seg + kRingBR - 1) / kRingBR) * kRingBR;
         if (seg < 32) seg = 32;
     }
+#ifdef B200SIFT_RING_SEG
+    seg = B200SIFT_RING_SEG;   // build-time sweep of the segment height
+#endif
     return launch_ring_s<R, SDEEP>(c, src, dst, dst2, n_img, h, w, pitch, img_stride, h2, w2, pitch2, img_stride2,
                                    tapset, seg);
 }
