@@ -54,6 +54,43 @@ def load_workload():
     return panorama_set(18, 512, 384), 'synthetic 18 x 384x512 panorama sequence'
 
 
+def mosaic_tiles():
+    """The 36 reference images (parrington + grail fixtures) the synthetic frames are tiled from."""
+    tiles = []
+    for name in ('parrington', 'grail'):
+        fx = os.path.join(ROOT, 'tests', 'golden', name + '.npz')
+        if os.path.exists(fx):
+            tiles += list(np.load(fx)['gray'])
+    if not tiles:
+        from vfx_image_stitching_b200.synthetic import natural_image
+        tiles = [natural_image(512, 384, 50 + i) for i in range(36)]
+    return tiles
+
+
+def int8_peak(torch, dev):
+    """Dense int8 tensor peak measured now on this GPU (cuBLASLt IGEMM 8192^3 through torch._int_mm, best of
+    8 launches): the denominator of the matcher's roofline fraction (it issues tcgen05.mma kind::i8)."""
+    try:
+        n = 8192
+        a = torch.randint(-8, 8, (n, n), dtype=torch.int8, device=dev)
+        b = torch.randint(-8, 8, (n, n), dtype=torch.int8, device=dev).t()
+        for _ in range(3):
+            torch._int_mm(a, b)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(8):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch._int_mm(a, b); e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best * 1e-3) / 1e12, 'measured in this run (torch._int_mm 8192^3, cuBLASLt IGEMM, best of 8)'
+    except Exception as e:   # noqa: BLE001
+        p = os.path.join(ROOT, 'profiles', 'r2_int8_peak.json')
+        if os.path.exists(p):
+            return float(json.load(open(p))['int8_tops']), f'profiles/r2_int8_peak.json (live probe failed: {e!r})'[:160]
+        return 2.0 * 1662.8, 'fallback: 2 x measured bf16 peak'
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -143,6 +180,24 @@ def cpu_run(imgs, steps, warmup, budget_s=150.0):
     return mpix / dt, dt * 1e3, sample, threads, pairs / dt
 
 
+def ncu_traffic(path):
+    """{radius: dram read + write bytes per launch} parsed from a committed ncu summary (profiles/*.txt)."""
+    import re
+    if not os.path.exists(path):
+        return None, f'{os.path.basename(path)} missing'
+    out, cur = {}, None
+    for ln in open(path):
+        m = re.match(r'== void blur_ring_kernel<(\d+),', ln)
+        if m:
+            cur = int(m.group(1))
+            out[cur] = 0.0
+        m = re.match(r'\s+dram__bytes_(read|write)\.sum\s+(\d+) byte', ln)
+        if m and cur is not None:
+            out[cur] += float(m.group(2))
+    ok = all(r in out for r in (5, 6, 8, 10, 13))
+    return (out if ok else None), f'parsed from profiles/{os.path.basename(path)} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)'
+
+
 def reference_arm(args, rank):
     if rank != 0:
         return
@@ -171,6 +226,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--depth', type=int, default=3, help='steps in flight per GPU (library contexts per rank)')
+    ap.add_argument('--no-extra', action='store_true', help='skip the frames (configs[3]) and matcher (configs[4]) legs')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     rank = int(os.environ.get('RANK', '0'))
@@ -334,6 +390,83 @@ def main():
         strong = {'ms_per_step': ms_s, 'value': nb * h * w / 1e6 / (ms_s / 1e3), 'unit': UNIT,
                   'sharding': '18 images in contiguous blocks over all ranks'}
 
+    # ---- BASELINE.json configs[3]: 64 synthetic 4096x3072 frames, detect+describe only, the frames split
+    # over the ranks (strong scaling, no exchange); configs[4]: the 64k x 64k matcher, A rows split over the
+    # ranks, B replicated (no reduction: the top-2 is per A row).  Both on every rank, max time over ranks.
+    import ctypes as C
+    frames_line = matcher_line = None
+    if not args.no_extra:
+        from vfx_image_stitching_b200.synthetic import descriptor_sets, mosaic_frame
+        tiles = mosaic_tiles()
+        f_lo, f_hi = panorama.shard_range(64, rank, world)
+        FB = 8                                            # frames per detect call
+        my_frames = [torch.from_numpy(mosaic_frame(f, tiles)).to(dev) for f in range(f_lo, f_hi)]
+        batches = [my_frames[i:i + FB] for i in range(0, len(my_frames), FB)]
+        from vfx_image_stitching_b200.pipeline import PanoramaPipeline
+        fpipe = PanoramaPipeline(contexts=all_ctx)
+
+        def run_frames(reps):
+            jobs = [b for _ in range(reps) for b in batches]
+            return fpipe.map(lambda b, c_: sift_impl.detect_and_describe_batch(b, ctx=c_, download=False), jobs)
+        if batches:
+            run_frames(1)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        FREPS = 2
+        e0.record()
+        fcounts = run_frames(FREPS) if batches else []
+        torch.cuda.synchronize()
+        e1.record()
+        torch.cuda.synchronize()
+        kp_local = float(sum(int(np.sum(cn)) for cn in fcounts[:len(batches)]))
+        t = torch.tensor([e0.elapsed_time(e1) / FREPS, kp_local], dtype=torch.float64, device=dev)
+        if world > 1:
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t[0] = tmax[0]
+        ms_f = float(t[0])
+        fpx = 64 * 3072 * 4096
+        frames_line = {
+            'workload': 'synthetic 64 x 4096x3072 RGB frames, detect+describe (BASELINE.json configs[3]); mosaic of the '
+                        'reference images (8 x 8 tiles of 384x512, SURVEY 8d variant i), frames split over the ranks',
+            'scaling': 'strong', 'frames_per_rank': -(-64 // world), 'frames_per_call': FB, 'ms': ms_f,
+            'value': fpx / 1e6 / (ms_f / 1e3), 'unit': UNIT, 'keypoints': int(float(t[1])),
+            'algorithmic_dense_bytes': 403 * fpx,
+            'dense_GBps_if_all_time_were_dense': 403 * fpx / (ms_f / 1e3) / 1e9,
+            'hbm_bound_ms': 403 * fpx / (peaks()[0] * 1e9) * 1e3 / world,
+            'inputs': 'resident in HBM (uint8 BGR); results stay on the device'}
+        del my_frames, batches
+        # matcher
+        g = np.load(os.path.join(ROOT, 'tests', 'golden', 'parrington.npz')) if os.path.exists(
+            os.path.join(ROOT, 'tests', 'golden', 'parrington.npz')) else None
+        NM = 65536
+        if g is not None:
+            pool = np.concatenate([g[f'desc_{i}'] for i in g['full_images'].tolist()])
+            A_all, B_all = descriptor_sets('real', NM, NM, pool)
+            dist_name = 'real-like: rows of the reference\'s parrington descriptors with +-2 jitter, seed 7'
+        else:
+            A_all, B_all = descriptor_sets('uniform', NM, NM)
+            dist_name = 'uniform, seed 8'
+        a_lo, a_hi = panorama.shard_range(NM, rank, world)
+        A_loc = np.ascontiguousarray(A_all[a_lo:a_hi])
+        msm = {}
+        for name_e, top2 in (('best', 0), ('top2', 1)):
+            ms = C.c_float()
+            if world > 1:
+                dist.barrier()
+            _capi.check(ctx.lib.b200sift_bench_match(ctx.handle, _capi.ptr(A_loc), len(A_loc), _capi.ptr(B_all), NM, top2, 10,
+                                                     C.byref(ms)))
+            tm = torch.tensor([ms.value], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            msm[name_e] = float(tm[0])
+        matcher_line = {'ms': msm, 'distribution': dist_name, 'nA': NM, 'nB': NM,
+                        'split': f'A rows in contiguous blocks over {world} rank(s), B replicated'}
+        fpipe.close()
+
     counts = np.asarray(out_e2e[1])
     desc_pairs = float(sum(int(counts[i]) * int(counts[i + 1]) for i in range(n - 1)))
     h2d = n * int(pinned_base[0].numel())                                   # whole job, all ranks
@@ -345,7 +478,6 @@ def main():
         # layer shape (18 x 1024 x 768 float32 per launch), timed alone with CUDA events.
         peak, peak_src = peaks()
         lib = ctx.lib
-        import ctypes as C
         detail = {}
         sig = sift_impl.generate_gaussian_kernels(1.6, 3)
         t_sum = 0.0
@@ -357,10 +489,25 @@ def main():
             t_sum += ms.value
         by = 8.0 * nb * (2 * h) * (2 * w)
         ach = by / (t_sum / 6) / 1e6      # bytes per launch / average launch duration over the 6 blurs
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch of blur_ring_kernel at this shape, from
-        # the ncu --set full capture summarised in profiles/r1_final_ring_small_ncu.txt (59.1-61.3 MB read +
-        # 10.7-12.6 MB written: the rest of the output is still dirty in L2 when the kernel ends)
-        traffic = {5: 70.9e6, 6: 70.9e6, 8: 70.6e6, 10: 70.7e6, 13: 73.9e6}
+        # the same bytes through a plain device copy (torch's copy kernel, the one MEASURED_PEAKS.json's
+        # hbm_gbs was taken with at 1 Gi elements) under the same protocol: what a launch of this size
+        # can reach at all (start-up, DRAM page opening and the drain are a fixed few microseconds)
+        ca = torch.empty(nb * 2 * h * 2 * w, dtype=torch.float32, device=dev).normal_()
+        cb = torch.empty_like(ca)
+        for _ in range(3):
+            cb.copy_(ca)
+        t_copy = 0.0
+        for i in range(10):
+            flush.fill_(i)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); cb.copy_(ca); e1.record()
+            torch.cuda.synchronize()
+            t_copy += e0.elapsed_time(e1) / 10
+        del ca, cb
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of blur_ring_kernel at this shape: read from
+        # the committed ncu summary of the same kernel (profiles/r1_final_ring_small_ncu.txt, unchanged this
+        # round); the output is still dirty in L2 when the kernel ends, hence less than the algorithmic bytes
+        traffic, traffic_src = ncu_traffic(os.path.join(ROOT, 'profiles', 'r1_final_ring_small_ncu.txt'))
         # the same kernel where the layer no longer fits one wave of CTAs (the 4096x3072-frame regime of
         # BASELINE.json configs[3]: 8 frames, octave-0 layers of 6144 x 8192): it is HBM-bound there
         large = {}
@@ -372,7 +519,11 @@ def main():
         roof = {'bound': 'hbm', 'kernel': 'blur_ring_kernel<R> (octave-0 layer shape; average over the base blur '
                                           'and the 5 layer blurs of one octave: R = 5, 5, 6, 8, 10, 13)',
                 'achieved': ach, 'peak': peak, 'unit': 'GB/s', 'frac': ach / peak,
-                'traffic': sum(traffic[r] for r in (5, 5, 6, 8, 10, 13)) / 6,
+                'traffic': (sum(traffic[r] for r in (5, 5, 6, 8, 10, 13)) / 6) if traffic else None,
+                'traffic_source': traffic_src,
+                'copy_same_bytes': {'ms': t_copy, 'GB/s': by / t_copy / 1e6, 'frac_of_peak': by / t_copy / 1e6 / peak,
+                                    'what': 'torch copy_ of 18 x 1024 x 768 float32 (same 8 B/px), L2 flushed: the ceiling '
+                                            'of a launch of this size'},
                 'algorithmic_bytes_per_launch': 8 * nb * 2 * h * 2 * w, 'peak_source': peak_src,
                 'timing': 'each launch alone between CUDA events on the launch stream, 256 MiB L2 flush before it',
                 'per_sigma': detail, 'large_shape_8x6144x8192': large}
@@ -406,6 +557,22 @@ def main():
         }
         if strong:
             line['strong_18_images'] = strong
+        if frames_line:
+            line['frames_64x4096x3072'] = frames_line
+        if matcher_line:
+            pk8, pk8_src = int8_peak(torch, dev)
+            ops = 2.0 * 128 * matcher_line['nA'] * matcher_line['nB']
+            tops = {k: ops / (v * 1e-3) / 1e12 for k, v in matcher_line['ms'].items()}
+            line['roofline_matcher'] = {
+                'bound': 'tensor', 'kernel': 'match_tc_kernel<false> (tcgen05.mma kind::i8, nearest-neighbour epilogue)',
+                'achieved': tops['best'], 'peak': pk8 * world, 'unit': 'TOP/s', 'frac': tops['best'] / (pk8 * world),
+                'peak_source': pk8_src + (f' x {world} GPUs' if world > 1 else ''),
+                'top2_epilogue': {'achieved': tops['top2'], 'frac': tops['top2'] / (pk8 * world)},
+                'algorithmic_ops_per_launch': ops, 'desc_pairs_per_s': matcher_line['nA'] * matcher_line['nB'] /
+                (matcher_line['ms']['best'] * 1e-3), 'frac_of_measured_bf16_peak': tops['best'] / (1662.8 * world),
+                'timing': 'kernel alone, mean of 10 launches between CUDA events on the launch stream (max over ranks); '
+                          'operands (8 MB + 8 MB) stay in L2 between launches by design: B is re-read by every A tile',
+                **{k: matcher_line[k] for k in ('distribution', 'nA', 'nB', 'split', 'ms')}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

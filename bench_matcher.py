@@ -38,7 +38,7 @@ def main():
     for na, nb in shapes:
         for top2 in (0, 1):
             ms = C.c_float()
-            _capi.check(ctx.lib.b200sift_bench_match(ctx.handle, na, nb, top2, a.iters, C.byref(ms)))
+            _capi.check(ctx.lib.b200sift_bench_match(ctx.handle, None, na, None, nb, top2, a.iters, C.byref(ms)))
             tops = 2.0 * 128 * na * nb / (ms.value * 1e-3) / 1e12
             rows.append({'nA': na, 'nB': nb, 'epilogue': 'top2' if top2 else 'best', 'ms': ms.value,
                          'Tops': tops, 'frac_of_measured_int8_peak': tops / peak_i8,

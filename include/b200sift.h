@@ -210,6 +210,15 @@ B200SIFT_API int b200sift_pack_exchange(b200sift_ctx *ctx, int image, const int3
 B200SIFT_API int b200sift_unpack_exchange(b200sift_ctx *ctx, const void *gathered, int world, int cap, int src,
                                           int32_t *headers, int32_t *image_index);
 
+/* The exchange without any host synchronisation: `wire` (device, (cap+1)*136 bytes in the format above,
+ * e.g. the buffer a neighbour's b200sift_pack_exchange output was received into) is appended as an extra
+ * image whose keypoint count min(header[0], cap) is read ON THE DEVICE: the rows are copied by a kernel
+ * that reads the header, the image is laid out with cap rows, and b200sift_match_pairs[_device] patches
+ * the real count into its tables before it packs.  `wire` must stay valid and unchanged until those calls
+ * have run.  The caller learns header[0] > cap (truncation) from its own collective and repeats with a
+ * larger cap.  Stream-ordered on the context stream. */
+B200SIFT_API int b200sift_append_exchange(b200sift_ctx *ctx, const void *wire, int cap, int32_t *image_index);
+
 /* b200sift_match_pairs whose result stays on the device: the voted (dx, dy) of pair p is written as two
  * doubles at dst + p*dst_stride bytes ((0,0) without matches) on the context stream, no host
  * synchronisation, so that it can feed a collective directly.  b200sift_get_pair_matches is not available
@@ -328,10 +337,12 @@ B200SIFT_API int b200sift_bench_blur(b200sift_ctx *ctx, int n_img, int h, int w,
                                      int flush_l2, float *ms_per_launch);
 
 /* Measurement hook for the matcher sweep (BASELINE.json config 5): runs `iters` launches of the
- * tensor-core matcher kernel alone on synthetic nA x nB uint8 descriptors resident in HBM
- * (already in the packed layout) and returns the mean device time per launch in ms.  top2 != 0
- * selects the nearest + second-nearest epilogue.  Algorithmic work: 2*128*nA*nB operations. */
-B200SIFT_API int b200sift_bench_match(b200sift_ctx *ctx, int nA, int nB, int top2, int iters, float *ms_per_launch);
+ * tensor-core matcher kernel alone on nA x nB uint8 descriptors resident in HBM (already in the
+ * packed layout) and returns the mean device time per launch in ms.  A / B = host (nA,128) / (nB,128)
+ * descriptors, or both NULL for an on-device synthetic fill.  top2 != 0 selects the nearest +
+ * second-nearest epilogue.  Algorithmic work: 2*128*nA*nB operations. */
+B200SIFT_API int b200sift_bench_match(b200sift_ctx *ctx, const uint8_t *A, int nA, const uint8_t *B, int nB, int top2,
+                                      int iters, float *ms_per_launch);
 
 #ifdef __cplusplus
 }

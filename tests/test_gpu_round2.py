@@ -87,24 +87,11 @@ def _oracle_match(oracle, A, B, threads=None):
 
 
 def _descriptor_sets(golden, kind, na, nb):
-    """The three distributions of SURVEY 8(d) config 5."""
-    if kind == 'real':      # rows of the reference's parrington descriptors, +-2 jitter, seed 7
-        g = golden('parrington')
-        pool = np.concatenate([g[f'desc_{i}'] for i in g['full_images'].tolist()]).astype(np.int16)
-        rng = np.random.default_rng(7)
-
-        def draw(n):
-            rows = pool[rng.integers(0, len(pool), n)]
-            return np.clip(rows + rng.integers(-2, 3, rows.shape), 0, 255).astype(np.uint8)
-        return draw(na), draw(nb)
-    rng = np.random.default_rng(8)
-    A = rng.integers(0, 256, (na, 128), dtype=np.uint8)
-    B = rng.integers(0, 256, (nb, 128), dtype=np.uint8)
-    if kind == 'ties':      # 1 % duplicated rows: exact ties, the lowest j must win
-        dup = rng.integers(0, nb, max(1, nb // 100))
-        B[dup] = B[rng.integers(0, nb, len(dup))]
-        A[rng.integers(0, na, max(1, na // 100))] = B[rng.integers(0, nb, max(1, na // 100))]
-    return A, B
+    """The three distributions of SURVEY 8(d) config 5 (synthetic.descriptor_sets, shared with the bench)."""
+    from vfx_image_stitching_b200.synthetic import descriptor_sets
+    g = golden('parrington')
+    pool = np.concatenate([g[f'desc_{i}'] for i in g['full_images'].tolist()])
+    return descriptor_sets(kind, na, nb, pool)
 
 
 @pytest.mark.parametrize('na,nb', [(16384, 16384), (2048, 65536)])

@@ -60,6 +60,7 @@ PROTOTYPES = {
     'b200sift_append_results': (_i, [_vp, _vp, _vp, _i, _i, _ip]),
     'b200sift_pack_exchange': (_i, [_vp, _i, _ip, _i, _vp, _i]),
     'b200sift_unpack_exchange': (_i, [_vp, _vp, _i, _i, _i, _ip, _ip]),
+    'b200sift_append_exchange': (_i, [_vp, _vp, _i, _ip]),
     'b200sift_match_pairs_device': (_i, [_vp, _i, _ip, _i, _d, _vp, _sz]),
     'b200sift_blend_two_images': (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _d, _d, C.POINTER(C.c_double), _i, _vp, _sz,
                                         _ip, _ip]),
@@ -78,7 +79,7 @@ PROTOTYPES = {
     'b200sift_remove_duplicates': (_i, [_vp, _vp, _i, _ip]),
     'b200sift_descriptors': (_i, [_vp, C.POINTER(Params), _vp, _i, _pp, _i, _i, _i, _i, _vp]),
     'b200sift_cylindrical_projection': (_i, [_vp, _vp, _i, _i, _i, _d, _vp]),
-    'b200sift_bench_match': (_i, [_vp, _i, _i, _i, _i, C.POINTER(C.c_float)]),
+    'b200sift_bench_match': (_i, [_vp, _vp, _i, _vp, _i, _i, _i, C.POINTER(C.c_float)]),
     'b200sift_bench_blur': (_i, [_vp, _i, _i, _i, _d, _i, _i, C.POINTER(C.c_float)]),
 }
 

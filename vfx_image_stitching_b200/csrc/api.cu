@@ -320,6 +320,7 @@ int b200sift_detect_describe(b200sift_ctx *c, const b200sift_params *params, int
     B200_ARG(P.num_intervals >= 1 && P.num_intervals + 3 <= kMaxLayers && P.sigma > 0);
     B200_CUDA(cudaSetDevice(c->device));
     c->have_results = false;
+    c->remote.clear();
     const size_t esz = dtype == B200SIFT_F32 ? 4 : 1;
     const size_t min_stride = (size_t)w * channels * esz;
     if (row_stride == 0) row_stride = min_stride;
@@ -693,6 +694,25 @@ __global__ void unpack_exchange_kernel(const uint8_t *__restrict__ src, int n_ro
     }
 }
 
+// same as unpack_exchange_kernel with the row count read from the buffer's header on the device
+__global__ void unpack_exchange_dev_kernel(const uint8_t *__restrict__ src, int cap, uint8_t *__restrict__ desc,
+                                           b200sift_keypoint *__restrict__ kps)
+{
+    const int n_rows = max(0, min(*reinterpret_cast<const int32_t *>(src), cap));
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = t / 17, wd = t - row * 17;
+    if (row >= n_rows) return;
+    const uint2 val = reinterpret_cast<const uint2 *>(src + (size_t)(row + 1) * kXRow)[wd];
+    if (wd < 16) {
+        reinterpret_cast<uint2 *>(desc + (size_t)row * 128)[wd] = val;
+    } else {
+        b200sift_keypoint k;
+        k.x = __uint_as_float(val.x); k.y = __uint_as_float(val.y);
+        k.size = 0.f; k.angle = 0.f; k.response = 0.f; k.octave = 0;
+        kps[row] = k;
+    }
+}
+
 __global__ void pair_shifts_kernel(const PairResult *__restrict__ res, int n, uint8_t *__restrict__ dst, size_t stride)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -788,6 +808,34 @@ int b200sift_unpack_exchange(b200sift_ctx *c, const void *gathered, int world, i
     }
     *image_index = c->n_img_last;
     c->img_off.push_back(used + n);
+    c->n_img_last += 1;
+    return 0;
+}
+
+int b200sift_append_exchange(b200sift_ctx *c, const void *wire, int cap, int32_t *image_index)
+{
+    B200_ARG(c && wire && image_index && cap >= 0);
+    if (!c->have_results) {
+        set_error("append_exchange before a successful detect_describe");
+        return B200SIFT_ESTATE;
+    }
+    B200_CUDA(cudaSetDevice(c->device));
+    const int used = c->img_off.back();
+    B200_CHECK(grow_results(c, used, used + cap));
+    if (cap > 0) {
+        const int threads = cap * 17;
+        unpack_exchange_dev_kernel<<<(threads + 255) / 256, 256, 0, c->stream>>>(
+            static_cast<const uint8_t *>(wire), cap, c->d_desc + (size_t)used * 128, c->d_kps + used);
+        c->launches++;
+        B200_CUDA(cudaGetLastError());
+    }
+    *image_index = c->n_img_last;
+    RemoteImage r;
+    r.image = c->n_img_last;
+    r.d_count = static_cast<const int32_t *>(wire);
+    r.cap = cap;
+    c->remote.push_back(r);
+    c->img_off.push_back(used + cap);   // laid out with the capacity; the matcher's tables get the real count
     c->n_img_last += 1;
     return 0;
 }
@@ -1206,11 +1254,12 @@ int b200sift_bench_blur(b200sift_ctx *c, int n_img, int h, int w, double sigma, 
     return 0;
 }
 
-int b200sift_bench_match(b200sift_ctx *c, int nA, int nB, int top2, int iters, float *ms_per_launch)
+int b200sift_bench_match(b200sift_ctx *c, const uint8_t *A, int nA, const uint8_t *B, int nB, int top2, int iters,
+                         float *ms_per_launch)
 {
-    B200_ARG(c && ms_per_launch && nA >= 1 && nB >= 1 && iters >= 1);
+    B200_ARG(c && ms_per_launch && nA >= 1 && nB >= 1 && iters >= 1 && ((A == nullptr) == (B == nullptr)));
     B200_CUDA(cudaSetDevice(c->device));
-    return bench_match_tc(c, nA, nB, top2, iters, ms_per_launch);
+    return bench_match_tc(c, A, nA, B, nB, top2, iters, ms_per_launch);
 }
 
 }  // extern "C"

@@ -114,7 +114,11 @@ struct RawKeypoint {
 };
 
 // one requested image pair of the batched matcher / its result
-struct PairDesc { int offA, nA, offB, nB; };
+struct PairDesc { int offA, nA, offB, nB, imgA, imgB; };
+// An image appended from a neighbour rank's exchange buffer (b200sift_append_exchange): its keypoint
+// count is only known on the device (header word of the wire buffer); the host lays it out with
+// `cap` rows and a kernel patches the real count into the matcher's tables.
+struct RemoteImage { int image; const int32_t *d_count; int cap; };
 struct PairResult { double dx, dy; int n_matches, best; float xyxy[4]; };
 
 struct DetectParams {
@@ -194,6 +198,7 @@ struct b200sift_ctx {
     int last_tiles_per_chunk = 0, last_n_chunks = 0;   // grid shape of the last tensor-core matcher launch
     std::vector<int> pair_counts;
     std::vector<b200::PairDesc> h_pair_desc;
+    std::vector<b200::RemoteImage> remote;      // device-counted images of the current result set
 };
 
 namespace b200 {
@@ -254,7 +259,8 @@ int run_match(b200sift_ctx *c, const uint8_t *dA, int nA, const uint8_t *dB, int
 int run_match_pairs(b200sift_ctx *c, int n_pairs, const int *h_pairs, int thresh, double vote_thr);
 int run_ratio_accept(b200sift_ctx *c, const int32_t *d_idx, const int32_t *d_d1, const int32_t *d_d2, int nA, int num,
                      int den, int32_t *d_ia, int32_t *d_ib, int32_t *d_count);
-int bench_match_tc(b200sift_ctx *c, int nA, int nB, int top2, int iters, float *ms_kernel);
+int bench_match_tc(b200sift_ctx *c, const uint8_t *hA, int nA, const uint8_t *hB, int nB, int top2, int iters,
+                   float *ms_kernel);
 int run_accept(b200sift_ctx *c, const int32_t *d_idx, const int32_t *d_d2, int nA, int thresh,
                const b200sift_keypoint *kA, const b200sift_keypoint *kB, int32_t *d_ia, int32_t *d_ib,
                float *d_xyxy, int32_t *d_count);

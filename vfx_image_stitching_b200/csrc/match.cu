@@ -84,6 +84,17 @@ int run_match(b200sift_ctx *c, const uint8_t *dA, int nA, const uint8_t *dB, int
 // ---------------------------------------------------------------------------
 constexpr int kFinThreads = 1024;
 
+// device-counted images (RemoteImage): the real keypoint count replaces the host's upper bound
+__global__ void __launch_bounds__(128)
+patch_remote_pairs_kernel(PairDesc *__restrict__ pd, int n_pairs, int image, const int32_t *__restrict__ d_count, int cap)
+{
+    const int n = max(0, min(*d_count, cap));
+    for (int p = threadIdx.x; p < n_pairs; p += blockDim.x) {
+        if (pd[p].imgA == image) pd[p].nA = n;
+        if (pd[p].imgB == image) pd[p].nB = n;
+    }
+}
+
 __global__ void __launch_bounds__(kFinThreads)
 pair_finalize_kernel(const PairDesc *__restrict__ pd, const int32_t *__restrict__ part, int n_chunks_max,
                      int rows_max, const b200sift_keypoint *__restrict__ kps, int thresh, double vote_thr,
@@ -177,7 +188,7 @@ int run_match_pairs(b200sift_ctx *c, int n_pairs, const int *h_pairs, int thresh
 {
     const int n_img = c->n_img_last;
     std::vector<PairDesc> &h_pd = c->h_pair_desc;  // read by an asynchronous copy below
-    h_pd.assign(n_pairs, PairDesc{0, 0, 0, 0});
+    h_pd.assign(n_pairs, PairDesc{0, 0, 0, 0, 0, 0});
     int rows_max = 1, nb_max = 0;
     for (int p = 0; p < n_pairs; ++p) {
         const int a = h_pairs[2 * p], b = h_pairs[2 * p + 1];
@@ -185,6 +196,8 @@ int run_match_pairs(b200sift_ctx *c, int n_pairs, const int *h_pairs, int thresh
         h_pd[p].nA = c->img_off[a + 1] - c->img_off[a];
         h_pd[p].offB = c->img_off[b];
         h_pd[p].nB = c->img_off[b + 1] - c->img_off[b];
+        h_pd[p].imgA = a;
+        h_pd[p].imgB = b;
         rows_max = h_pd[p].nA > rows_max ? h_pd[p].nA : rows_max;
         nb_max = h_pd[p].nB > nb_max ? h_pd[p].nB : nb_max;
     }
@@ -210,6 +223,10 @@ int run_match_pairs(b200sift_ctx *c, int n_pairs, const int *h_pairs, int thresh
     c->pair_n = n_pairs;
     c->d_pair_res = res; c->d_pair_ia = m_ia; c->d_pair_ib = m_ib; c->d_pair_xy = m_xy;
     B200_CUDA(cudaMemcpyAsync(pd, h_pd.data(), sizeof(PairDesc) * n_pairs, cudaMemcpyHostToDevice, c->stream));
+    for (const RemoteImage &r : c->remote) {
+        patch_remote_pairs_kernel<<<1, 128, 0, c->stream>>>(pd, n_pairs, r.image, r.d_count, r.cap);
+        c->launches++;
+    }
     {
         std::vector<int> off(n_img), cnt(n_img);
         for (int i = 0; i < n_img; ++i) { off[i] = c->img_off[i]; cnt[i] = c->img_off[i + 1] - c->img_off[i]; }

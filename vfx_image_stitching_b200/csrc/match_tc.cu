@@ -160,7 +160,21 @@ pack_kernel(const uint8_t *__restrict__ src, const PackImg *__restrict__ imgs, u
 }
 
 // ------------------------------------------------------------------ the matcher
-struct TcPair { int offA, nA, offB, nB; };  // packed row offsets (multiples of 256) and true counts
+struct TcPair { int offA, nA, offB, nB, imgA, imgB; };  // packed row offsets (multiples of 256), true counts, image indices
+
+// Device-counted images (RemoteImage): write min(*d_count, cap) over the host's upper bound in the
+// pack table and in every pair that names the image.  Runs after the table upload, before pack_kernel.
+__global__ void __launch_bounds__(128)
+patch_remote_tc_kernel(PackImg *__restrict__ imgs, TcPair *__restrict__ tp, int n_pairs, int image,
+                       const int32_t *__restrict__ d_count, int cap)
+{
+    const int n = max(0, min(*d_count, cap));
+    if (threadIdx.x == 0) imgs[image].n = n;
+    for (int p = threadIdx.x; p < n_pairs; p += blockDim.x) {
+        if (tp[p].imgA == image) tp[p].nA = n;
+        if (tp[p].imgB == image) tp[p].nB = n;
+    }
+}
 
 template <bool kTop2>
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -378,8 +392,8 @@ int run_match_tc(b200sift_ctx *c, const uint8_t *d_src, int n_imgs, const int *h
     std::vector<TcPair> tp(n_pairs);
     for (int p = 0; p < n_pairs; ++p) {
         const int a = h_pairs[2 * p], b = h_pairs[2 * p + 1];
-        tp[p].offA = imgs[a].dst_off; tp[p].nA = imgs[a].n;
-        tp[p].offB = imgs[b].dst_off; tp[p].nB = imgs[b].n;
+        tp[p].offA = imgs[a].dst_off; tp[p].nA = imgs[a].n; tp[p].imgA = a;
+        tp[p].offB = imgs[b].dst_off; tp[p].nB = imgs[b].n; tp[p].imgB = b;
     }
     size_t cap = c->tc_cap;
     const size_t need = (size_t)total * 128 + (size_t)total * 8 + imgs.size() * sizeof(PackImg) +
@@ -397,6 +411,11 @@ int run_match_tc(b200sift_ctx *c, const uint8_t *d_src, int n_imgs, const int *h
     memcpy(c->h_tc_tables.data() + imgs.size() * sizeof(PackImg), tp.data(), tp.size() * sizeof(TcPair));
     B200_CUDA(cudaMemcpyAsync(d_imgs, c->h_tc_tables.data(), c->h_tc_tables.size(), cudaMemcpyHostToDevice,
                               c->stream));  // d_imgs and d_tp are adjacent
+    for (const RemoteImage &r : c->remote)
+        if (d_src == c->d_desc && r.image < n_imgs) {
+            patch_remote_tc_kernel<<<1, 128, 0, c->stream>>>(d_imgs, d_tp, n_pairs, r.image, r.d_count, r.cap);
+            c->launches++;
+        }
     if (max_pad > 0) {
         dim3 pg((max_pad * 8 + 255) / 256, n_imgs);
         pack_kernel<<<pg, 256, 0, c->stream>>>(d_src, d_imgs, packed, nrm, ckey);
@@ -441,12 +460,18 @@ __global__ void __launch_bounds__(256) fill_desc_kernel(uint8_t *d, size_t n_byt
 // Times the tensor-core kernel alone (CUDA events on the context stream) on synthetic nA x nB
 // descriptors resident in HBM; `ms_kernel` = mean per launch.  Algorithmic work of one launch:
 // 2*128*nA*nB integer operations.
-int bench_match_tc(b200sift_ctx *c, int nA, int nB, int top2, int iters, float *ms_kernel)
+int bench_match_tc(b200sift_ctx *c, const uint8_t *hA, int nA, const uint8_t *hB, int nB, int top2, int iters,
+                   float *ms_kernel)
 {
     size_t cap = c->tcsrc_cap;
     B200_CHECK(ensure(&c->d_tcsrc, &cap, (size_t)(nA + nB) * 128));
     c->tcsrc_cap = cap;
-    fill_desc_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_tcsrc, (size_t)(nA + nB) * 128, 12345u);
+    if (hA && hB) {   // caller-supplied descriptors (host): the distributions of BASELINE.json configs[4]
+        B200_CUDA(cudaMemcpyAsync(c->d_tcsrc, hA, (size_t)nA * 128, cudaMemcpyHostToDevice, c->stream));
+        B200_CUDA(cudaMemcpyAsync(c->d_tcsrc + (size_t)nA * 128, hB, (size_t)nB * 128, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        fill_desc_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->d_tcsrc, (size_t)(nA + nB) * 128, 12345u);
+    }
     int tpc, n_chunks;
     tc_chunking(c, nA, nB, 1, &tpc, &n_chunks);
     cap = c->mout_cap;

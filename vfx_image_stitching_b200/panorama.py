@@ -3,10 +3,11 @@
 One process per GPU (torch.distributed; NCCL over NVLink on the GPU box, gloo in the CPU tests).
 detect+describe is independent per image and matching is independent per adjacent pair (SURVEY
 8e), so images are split into contiguous blocks in pano order and pair (i, i+1) belongs to the
-rank that owns image i.  The only data-path collective is ONE all-gather of every rank's FIRST
-image's descriptors (uint8) + keypoint coordinates: the right-hand side of the previous rank's
-boundary pair.  Results are identical for any world size because every image and every pair is
-computed by exactly one rank with the same kernels.
+rank that owns image i.  The only data-path exchange is a neighbour transfer: every rank sends its
+FIRST image's descriptors (uint8) + keypoint coordinates to the previous rank (NCCL send / recv over
+NVLink), the right-hand side of that rank's boundary pair; the voted shifts and keypoint counts are
+then all-gathered (24 bytes per image).  Results are identical for any world size because every
+image and every pair is computed by exactly one rank with the same kernels.
 
 The compute sits behind a small backend interface so that the plumbing can be exercised on CPU
 with gloo (tests/test_distributed_gloo.py plugs the oracle in); `GpuBackend` is the product.
@@ -39,9 +40,9 @@ class BackendBase:
     """What sharded_panorama_shifts needs from the compute side.
 
     A backend implements the four primitives detect / first_image / append_remote / match_pairs;
-    the three exchange steps below are then provided with plain tensor operations (this is what
-    the gloo tests run, with the oracle as compute).  GpuBackend overrides the exchange steps with
-    single kernels of the C library."""
+    the three exchange steps below (pack_first, append_exchange, match_pairs_into) are then provided
+    with plain tensor operations (this is what the gloo tests run, with the oracle as compute).
+    GpuBackend overrides them with single calls into the C library."""
 
     def stream_ctx(self, device):
         """Context manager under which the exchange (tensor operations + collectives) runs."""
@@ -70,19 +71,14 @@ class BackendBase:
             row[1:1 + m, :128].copy_(d[:m])
             row[1:1 + m, 128:].copy_(xy[:m].contiguous().view(torch.uint8).view(m, 8))
 
-    def unpack(self, gathered, world, cap, src):
-        """-> (headers int32 (world, 34) on the host, local index of block `src` appended as an
-        extra image, or None when src < 0 or the block was truncated on the wire)."""
+    def append_exchange(self, recv, cap):
+        """Make the image in the wire buffer `recv` ((cap+1, 136) uint8: header row + keypoint rows, as
+        pack_first wrote it on the sending rank) matchable; returns its local image index."""
         import torch
-        g3 = gathered.view(world, cap + 1, ROW_BYTES)
-        hdr = g3[:, 0, :].contiguous().cpu().view(torch.int32).numpy().reshape(world, HDR_INTS)
-        idx = None
-        if src >= 0 and int(hdr[src, 0]) <= cap:
-            m = int(hdr[src, 0])
-            r_desc = g3[src, 1:1 + m, :128].contiguous()
-            r_xy = g3[src, 1:1 + m, 128:].contiguous().view(torch.float32).view(m, 2)
-            idx = self.append_remote(r_desc, r_xy)
-        return hdr, idx
+        m = min(int(recv[0, :4].cpu().view(torch.int32)[0]), cap)
+        r_desc = recv[1:1 + m, :128].contiguous()
+        r_xy = recv[1:1 + m, 128:].contiguous().view(torch.float32).view(m, 2)
+        return self.append_remote(r_desc, r_xy)
 
     def match_pairs_into(self, pairs, ransac_thr, desc_thresh, res):
         """Voted (dx, dy) of local pair p into res[p, 0:2] (float64 tensor on the exchange device)."""
@@ -142,9 +138,9 @@ class GpuBackend(BackendBase):
         return iss.match_pairs(pairs, ransac_thr, desc_thresh, self.ctx)[0]
 
     # ---- exchange steps as single library calls.  The whole exchange -- these kernels, the tensor
-    # copies and both NCCL collectives -- runs on the CONTEXT's stream (torch.distributed issues on the
-    # current torch stream), so no events or cross-stream waits are needed; the only host
-    # synchronisations are the header read-back inside unpack and the final result download.
+    # copies, the neighbour send / recv and the result all-gather -- runs on the CONTEXT's stream
+    # (torch.distributed orders its work against the current torch stream), so no events or
+    # cross-stream waits are needed and nothing synchronises with the host until _finish().
     def close(self):
         import torch
         BackendBase.close(self)
@@ -165,15 +161,13 @@ class GpuBackend(BackendBase):
             return BackendBase.pack_first(self, row, cap, tail, device)   # empty block: header only
         check(self.ctx.lib.b200sift_pack_exchange(self.ctx.handle, 0, t, len(tail), C.c_void_p(row.data_ptr()), cap))
 
-    def unpack(self, gathered, world, cap, src):
+    def append_exchange(self, recv, cap):
+        """No host synchronisation: the count in the header is read on the device (b200sift_append_exchange)."""
         from ._capi import check
-        if len(self.counts) == 0:
-            return BackendBase.unpack(self, gathered, world, cap, -1)
-        hdr = np.zeros((world, HDR_INTS), np.int32)
         idx = C.c_int32(-1)
-        check(self.ctx.lib.b200sift_unpack_exchange(self.ctx.handle, C.c_void_p(gathered.data_ptr()), world, cap,
-                                                    src, hdr.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(idx)))
-        return hdr, (idx.value if idx.value >= 0 else None)
+        check(self.ctx.lib.b200sift_append_exchange(self.ctx.handle, C.c_void_p(recv.data_ptr()), int(cap),
+                                                    C.byref(idx)))
+        return idx.value
 
     def match_pairs_into(self, pairs, ransac_thr, desc_thresh, res):
         from . import image_stitching_sift as iss
@@ -191,7 +185,6 @@ class GpuBackend(BackendBase):
 def sharded_panorama_shifts(images, backend, ransac_thr=3, desc_thresh=25000, dist=None, device='cpu'):
     """All adjacent-pair shifts of `images` (every rank passes the same list; each rank only
     touches its block).  Returns on every rank (shifts [(dx,dy)] * (n-1), keypoint counts [n])."""
-    import torch
     n = len(images)
     if dist is None or not dist.is_initialized():
         rank, world = 0, 1
@@ -200,45 +193,62 @@ def sharded_panorama_shifts(images, backend, ransac_thr=3, desc_thresh=25000, di
     lo, hi = shard_range(n, rank, world)
     counts_local = np.asarray(backend.detect([images[i] for i in range(lo, hi)]), np.int64)
     _mark('detect')
-    with backend.stream_ctx(device):
-        return _exchange_and_match(images, backend, ransac_thr, desc_thresh, dist, device, rank, world, lo, hi, n,
-                                   counts_local)
+    while True:
+        with backend.stream_ctx(device):
+            pending = _exchange_and_match(backend, ransac_thr, desc_thresh, dist, device, rank, world, lo, hi, n,
+                                          counts_local)
+        res = _finish(pending)
+        if res is not None:
+            return res
+        # a first image did not fit the exchange rows: every rank saw the same counts and grew its buffers
 
 
-def _exchange_and_match(images, backend, ransac_thr, desc_thresh, dist, device, rank, world, lo, hi, n, counts_local):
+def _exchange_state(backend, world, device):
+    st = getattr(backend, '_xchg', None)
+    if st is None or st['world'] != world or st['device'] != str(device):
+        st = backend._xchg = {'world': world, 'device': str(device), 'cap': 0, 'want_cap': MIN_EXCHANGE_ROWS}
+    return st
+
+
+def _exchange_and_match(backend, ransac_thr, desc_thresh, dist, device, rank, world, lo, hi, n, counts_local):
+    """Stage 2 of one image set, ENQUEUED on the backend's stream; returns a handle for _finish().
+
+    Exchange: a rank needs one remote image, the first image of the next rank (right-hand side of its
+    block-boundary pair).  Every rank packs its first image into wire rows of 136 bytes (128 B descriptor
+    + 8 B xy; row 0 is a header with the keypoint count) and SENDS them to its left neighbour -- a
+    point-to-point transfer over NVLink, not an all-gather.  The receiver appends the buffer as an extra
+    image whose count is read from the header on the device, so the exchange involves no host
+    synchronisation.  Result: per image (dx, dy, keypoint count), one tiny all-gather, copied to pinned
+    host memory asynchronously; _finish() waits for it.  If a first image had more keypoints than the wire
+    buffer has rows, every rank sees that in the gathered counts, grows the buffer and repeats the set."""
     import torch
-
-    # ---- exchange: first image of every rank in ONE all-gather.  A keypoint travels as a 136-byte
-    # row (128 B descriptor + 8 B xy); row 0 is a header (count, lo, block length), so no separate
-    # count exchange is needed.  The row capacity is agreed implicitly: every rank sees every
-    # header, and if some count exceeds the current capacity all ranks grow it and repeat.
     remote_idx = None
+    st = None
     if world > 1:
-        st = getattr(backend, '_xchg', None)
-        if st is None or st['world'] != world or st['device'] != str(device):
-            st = backend._xchg = {'world': world, 'device': str(device), 'cap': 0}
-        cap = max(st['cap'], MIN_EXCHANGE_ROWS)
+        st = _exchange_state(backend, world, device)
+        cap = max(st['want_cap'], MIN_EXCHANGE_ROWS)
+        if st['cap'] != cap:
+            st['cap'] = cap
+            st['row'] = torch.zeros((cap + 1, ROW_BYTES), dtype=torch.uint8, device=device)
+            st['recv'] = torch.zeros((cap + 1, ROW_BYTES), dtype=torch.uint8, device=device)
         # blocks are contiguous and empty blocks only occur at the tail, so the owner of image `hi`
-        # is simply the next rank
+        # is simply the next rank, and whoever owns a block sends its first image to the previous rank
         src = rank + 1 if (hi > lo and hi < n) else -1
-        while True:
-            if st['cap'] != cap:
-                st['cap'] = cap
-                st['row'] = torch.zeros((cap + 1, ROW_BYTES), dtype=torch.uint8, device=device)
-                st['all'] = torch.zeros((world * (cap + 1), ROW_BYTES), dtype=torch.uint8, device=device)
+        dst = rank - 1 if (hi > lo and rank > 0) else -1
+        ops = []
+        if dst >= 0:
             backend.pack_first(st['row'], cap, (lo, hi - lo), device)
-            _mark('x.pack')
-            dist.all_gather_into_tensor(st['all'], st['row'])       # the one data-path collective
-            _mark('x.gather')
-            hdr, remote_idx = backend.unpack(st['all'], world, cap, src)
-            need = int(hdr[:, 0].max())
-            if need <= cap:
-                break
-            cap = 1 << (need - 1).bit_length()               # same decision on every rank
-        cnts = hdr[:, :3]
+            ops.append(dist.P2POp(dist.isend, st['row'], dst))
+        if src >= 0:
+            ops.append(dist.P2POp(dist.irecv, st['recv'], src))
+        _mark('x.pack')
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()                                   # stream-ordered on CUDA, blocking on CPU (gloo)
+        _mark('x.sendrecv')
+        if src >= 0:
+            remote_idx = backend.append_exchange(st['recv'], cap)
         _mark('exchange')
-    else:
-        cnts = np.array([[0, lo, hi - lo]])
 
     # ---- owned pairs in one batched device pass, results to every rank (tiny): per image
     # (dx, dy, keypoint count)
@@ -247,7 +257,7 @@ def _exchange_and_match(images, backend, ransac_thr, desc_thresh, dist, device, 
         if i + 1 < n:
             pairs.append((i - lo, i + 1 - lo) if i + 1 < hi else (i - lo, remote_idx))
     if world > 1:
-        maxb = max(1, int(cnts[:, 2].max()))
+        maxb = (n + world - 1) // world                      # largest block (shard_range)
         if st.get('maxb') != maxb:
             st['maxb'] = maxb
             st['res_h'] = torch.zeros((maxb, 3), dtype=torch.float64)
@@ -263,16 +273,39 @@ def _exchange_and_match(images, backend, ransac_thr, desc_thresh, dist, device, 
         backend.match_pairs_into(pairs, ransac_thr, desc_thresh, st['res_d'])
         _mark('match')
         dist.all_gather_into_tensor(st['out_d'], st['res_d'])
-        st['out_h'].copy_(st['out_d'])                      # synchronous: the results are on the host now
-        out = st['out_h'].numpy().reshape(world, maxb, 3)
-        rows = np.concatenate([out[r, :int(cnts[r, 2])] for r in range(world)], 0)
+        st['out_h'].copy_(st['out_d'], non_blocking=True)
+        ev = None
+        if torch.device(device).type == 'cuda':
+            ev = torch.cuda.Event()
+            ev.record()
+        return {'st': st, 'event': ev, 'n': n, 'world': world, 'maxb': maxb, 'cap': st['cap']}
+    rows = np.zeros((max(hi - lo, 0), 3), np.float64)
+    if hi > lo:
+        rows[:, 2] = counts_local
+    if pairs:
+        for p, sft in enumerate(backend.match_pairs(pairs, ransac_thr, desc_thresh)):
+            rows[p, 0], rows[p, 1] = sft
+    return {'rows': rows, 'n': n}
+
+
+def _finish(pending):
+    """Wait for the results of an enqueued stage 2; returns (shifts, counts), or None when the exchange
+    rows were too few for some first image (the wire capacity has then been raised: repeat the set)."""
+    n = pending['n']
+    if 'rows' in pending:
+        rows = pending['rows']
     else:
-        rows = np.zeros((max(hi - lo, 0), 3), np.float64)
-        if hi > lo:
-            rows[:, 2] = counts_local
-        if pairs:
-            for p, sft in enumerate(backend.match_pairs(pairs, ransac_thr, desc_thresh)):
-                rows[p, 0], rows[p, 1] = sft
+        st, world, maxb = pending['st'], pending['world'], pending['maxb']
+        if pending['event'] is not None:
+            pending['event'].synchronize()
+        out = st['out_h'].numpy().reshape(world, maxb, 3)
+        blocks = [shard_range(n, r, world) for r in range(world)]
+        rows = np.concatenate([out[r, :b[1] - b[0]] for r, b in enumerate(blocks)], 0)
+        first_counts = [int(out[r, 0, 2]) for r, b in enumerate(blocks) if b[1] > b[0] and r > 0]
+        need = max(first_counts) if first_counts else 0
+        if need > pending['cap']:
+            st['want_cap'] = 1 << (need - 1).bit_length()        # same decision on every rank
+            return None
     _mark('results')
     shifts = [(float(rows[i, 0]), float(rows[i, 1])) for i in range(n - 1)]
     return shifts, rows[:, 2].astype(np.int64).tolist()
@@ -283,12 +316,13 @@ def sharded_panorama_stream(jobs, backends, ransac_thr=3, desc_thresh=25000, dis
 
     Two stages per job: (1) detect+describe of the local block -- no communication, runs on a helper
     thread; (2) exchange + matching + result all-gather -- every collective is issued from the calling
-    thread, in job order, so all ranks issue them in the same order.  Job k uses backends[k % len(backends)]
-    (one library context each): while stage 2 of job k runs, stage 1 of the next len(backends) - 1 jobs is
-    already on the GPU with the other contexts.  With a single backend there is nothing to overlap with:
-    the two stages of every job run one after the other on the calling thread.  `after(k, backend, shifts, counts)` (optional) runs in the calling thread after job
-    k, e.g. to download its results.  Returns [(shifts, counts)] per job -- identical to calling
-    sharded_panorama_shifts job by job."""
+    thread, in job order, so all ranks issue them in the same order.  Stage 2 is only ENQUEUED (no host
+    synchronisation inside); its results are collected one job later, after stage 2 of the next job has
+    been queued, so the wait and `after(k, backend, shifts, counts)` (optional, e.g. the download of job
+    k's keypoints) overlap device work.  Job k uses backends[k % len(backends)] (one library context
+    each); a context is handed to a new stage 1 only after its previous job has been collected.  With a
+    single backend there is nothing to overlap with: every job runs start to finish on the calling thread.
+    Returns [(shifts, counts)] per job -- identical to calling sharded_panorama_shifts job by job."""
     from concurrent.futures import ThreadPoolExecutor
     jobs = list(jobs)
     n_be = len(backends)
@@ -302,30 +336,33 @@ def sharded_panorama_stream(jobs, backends, ransac_thr=3, desc_thresh=25000, dis
         lo, hi = shard_range(len(images), rank, world)
         return lo, hi, np.asarray(backends[k % n_be].detect([images[i] for i in range(lo, hi)]), np.int64)
 
-    out = []
-    ahead = n_be - 1   # stage-1 jobs in flight next to stage 2 of job k: backends (k+1..k+ahead) % n_be, all != k % n_be
-    if ahead == 0:     # one context: stage 1 of job k+1 would overwrite what stage 2 of job k still reads
+    def stage2(k, lo, hi, counts_local):
+        be = backends[k % n_be]
+        with be.stream_ctx(device):
+            return _exchange_and_match(be, ransac_thr, desc_thresh, dist, device, rank, world, lo, hi, len(jobs[k]),
+                                       counts_local)
+
+    def collect(k, s1, pending):
+        res = _finish(pending)
+        while res is None:                         # wire capacity grown: repeat this set's stage 2
+            res = _finish(stage2(k, *s1))
+        if after is not None:
+            after(k, backends[k % n_be], *res)
+        return res
+
+    out = [None] * len(jobs)
+    lag = min(1, n_be - 1)     # jobs whose collection is deferred behind the next job's stage 2
+    with ThreadPoolExecutor(n_be) as pool:
+        futs = {k: pool.submit(stage1, k) for k in range(min(n_be, len(jobs)))}
+        waiting = []           # (k, stage-1 result, handle) not yet collected
         for k in range(len(jobs)):
-            lo, hi, counts_local = stage1(k)
-            be = backends[0]
-            with be.stream_ctx(device):
-                res = _exchange_and_match(jobs[k], be, ransac_thr, desc_thresh, dist, device, rank, world, lo, hi,
-                                          len(jobs[k]), counts_local)
-            if after is not None:
-                after(k, be, *res)
-            out.append(res)
-        return out
-    with ThreadPoolExecutor(ahead) as pool:
-        futs = {k: pool.submit(stage1, k) for k in range(min(ahead, len(jobs)))}
-        for k in range(len(jobs)):
-            lo, hi, counts_local = futs.pop(k).result()
-            if k + ahead < len(jobs):
-                futs[k + ahead] = pool.submit(stage1, k + ahead)   # its context finished stage 2 of job k-1
-            be = backends[k % n_be]
-            with be.stream_ctx(device):
-                res = _exchange_and_match(jobs[k], be, ransac_thr, desc_thresh, dist, device, rank, world, lo, hi,
-                                          len(jobs[k]), counts_local)
-            if after is not None:
-                after(k, be, *res)
-            out.append(res)
+            s1 = futs.pop(k).result()
+            waiting.append((k, s1, stage2(k, *s1)))
+            while len(waiting) > lag:
+                j, s1j, pend = waiting.pop(0)
+                out[j] = collect(j, s1j, pend)
+                if j + n_be < len(jobs):           # the context of job j is free again
+                    futs[j + n_be] = pool.submit(stage1, j + n_be)
+        for j, s1j, pend in waiting:
+            out[j] = collect(j, s1j, pend)
     return out

@@ -49,3 +49,39 @@ def panorama_set(n_images=18, h=512, w=384, seed=1000, shift=(-3, -245)):
         v = scene[y0:y0 + h, x0:x0 + w]
         out.append(np.ascontiguousarray(np.repeat(v[:, :, None], 3, axis=2)))
     return out
+
+
+def mosaic_frame(frame, tiles, rows=8, cols=8):
+    """BASELINE.json configs[3], variant (i) of SURVEY 8(d): a 3072 x 4096 BGR frame tiled 8 x 8 from the
+    repo's 384 x 512 images rotated by 90 degrees; tile (r, c) of frame f is image (f + 8 r + c) mod len(tiles).
+    `tiles`: list of 2-D uint8 images of identical shape (the cylindrically projected parrington + grail
+    images of tests/golden/*.npz, 512 rows x 384 cols each).  Natural-image content: ~1.5 k keypoints per tile."""
+    th, tw = tiles[0].shape[1], tiles[0].shape[0]          # after rot90: 384 rows x 512 cols
+    out = np.empty((rows * th, cols * tw), np.uint8)
+    for r in range(rows):
+        for c in range(cols):
+            t = np.rot90(tiles[(frame + cols * r + c) % len(tiles)])
+            out[r * th:(r + 1) * th, c * tw:(c + 1) * tw] = t
+    return np.ascontiguousarray(np.repeat(out[:, :, None], 3, axis=2))
+
+
+def descriptor_sets(kind, na, nb, pool=None, seed=None):
+    """The descriptor distributions of BASELINE.json configs[4]: 'real' -- rows of `pool`
+    (reference descriptors) with +-2 jitter, seed 7; 'uniform' -- rng.integers(0, 256), seed 8; 'ties' --
+    uniform with 1 % duplicated rows (exact ties: the lowest j must win)."""
+    if kind == 'real':
+        rng = np.random.default_rng(7 if seed is None else seed)
+        pool = np.asarray(pool).astype(np.int16)
+
+        def draw(n):
+            rows = pool[rng.integers(0, len(pool), n)]
+            return np.clip(rows + rng.integers(-2, 3, rows.shape), 0, 255).astype(np.uint8)
+        return draw(na), draw(nb)
+    rng = np.random.default_rng(8 if seed is None else seed)
+    A = rng.integers(0, 256, (na, 128), dtype=np.uint8)
+    B = rng.integers(0, 256, (nb, 128), dtype=np.uint8)
+    if kind == 'ties':
+        dup = rng.integers(0, nb, max(1, nb // 100))
+        B[dup] = B[rng.integers(0, nb, len(dup))]
+        A[rng.integers(0, na, max(1, na // 100))] = B[rng.integers(0, nb, max(1, na // 100))]
+    return A, B
