@@ -12,12 +12,12 @@ A "step" = one pass of the hot path over the 18-image set: detect+describe of ev
 (each image once) + brute-force matching and the translation vote of the 17 adjacent pairs.
 At N > 1 GPUs the job is a chain of N such sets (18 N images in pano order, 18 N - 1 adjacent
 pairs), sharded in contiguous blocks of 18 images per rank: per-GPU work is fixed ("weak"
-scaling), block-boundary pairs need the neighbour rank's first image (one all-gather).  The
+scaling), block-boundary pairs need the neighbour rank's first image (one NCCL send / recv).  The
 strong-scaling time of the single 18-image set over N ranks is reported next to it
 (`strong_18_images`).
-`value`  : inputs already resident in HBM; throughput over K steps with two steps in flight per GPU
-           (two library contexts per rank: the host round trips of one step overlap the kernels of
-           the other), device-timed with CUDA events around all K steps.
+`value`  : inputs already resident in HBM; throughput over K steps with --depth steps in flight per GPU
+           (one library context per step in flight: the host round trips of one step overlap the kernels
+           of the others), device-timed with CUDA events around all K steps.
 `e2e`    : the same through the drop-in API with pinned HOST images in, host keypoints /
            descriptors / shifts out (H2D + D2H inside the timed region).
 `single_step`: one step at a time on one context (the latency of a single call), per-step events.
@@ -225,7 +225,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--depth', type=int, default=3, help='steps in flight per GPU (library contexts per rank)')
+    ap.add_argument('--depth', type=int, default=4, help='steps in flight per GPU (library contexts per rank)')
     ap.add_argument('--no-extra', action='store_true', help='skip the frames (configs[3]) and matcher (configs[4]) legs')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
@@ -245,11 +245,21 @@ def main():
     dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        # NCCL_DEBUG stays as the caller set it: the driver reads the communicator's init lines.  Its
-        # banner would share stdout with the JSON line, so it is sent to stderr unless the caller chose a file.
-        if os.environ.get('NCCL_DEBUG') and not os.environ.get('NCCL_DEBUG_FILE'):
-            os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr'
-        dist.init_process_group('nccl', device_id=dev)
+        # NCCL_DEBUG stays as the caller set it: the driver reads the communicator's init lines.  NCCL
+        # prints its version banner (NCCL_DEBUG=VERSION, the default of this image) and, without
+        # NCCL_DEBUG_FILE, its INFO lines to stdout; stdout is the channel of the one JSON line, so file
+        # descriptor 1 points at stderr while the communicator is created (eager with device_id) and used once.
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group('nccl', device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
     ctx = _capi.default_context(local)
     stream = torch.cuda.Stream(dev)
     ctx.set_stream(stream.cuda_stream)
@@ -540,7 +550,8 @@ def main():
                        'chain': f'{world} such set(s) chained in pano order ({n} images, {n - 1} pairs): per-GPU work is fixed',
                        'images': n, 'pairs': n - 1, 'keypoints': int(counts.sum()),
                        'sharding': f'contiguous blocks of {nb} images per rank over {world} rank(s); pair (i,i+1) on the '
-                                   'owner of i; one all-gather of every block\'s first-image descriptors',
+                                   'owner of i; every rank sends its first image\'s descriptors to the previous rank (NCCL send / recv), '
+                                   'shifts and counts are all-gathered (24 B per image)',
                        'mode': f'throughput: {DEPTH} steps in flight per GPU ({DEPTH} library contexts per rank; N = 1: '
                                'pipeline.PanoramaPipeline, N > 1: panorama.sharded_panorama_stream); device time over all '
                                'steps / steps.  single_step = one step at a time, per-step CUDA events',
