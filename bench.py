@@ -560,7 +560,7 @@ def main():
             'e2e': {'value': mpix_step / (ms_e2e / 1e3), 'unit': UNIT, 'ms_per_step': ms_e2e,
                     'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'wall_ms_per_step': wall_e2e},
-            'gpu_launches': launches, 'wall_ms_per_step': wall_dev,
+            'gpu_launches': launches, 'wall_ms_per_step': wall_dev, 'host_cpus': os.cpu_count(),
             'single_step': {'ms_per_step': ms_one, 'value': mpix_step / (ms_one / 1e3), 'unit': UNIT,
                             'gpu_launches': launches_one},
             'match_desc_pairs_per_s': desc_pairs / (ms_dev / 1e3), 'image_pairs_per_s': (n - 1) / (ms_dev / 1e3),

@@ -45,6 +45,7 @@ PROTOTYPES = {
     'b200sift_destroy': (None, [_vp]),
     'b200sift_set_stream': (_i, [_vp, _vp]),
     'b200sift_get_stream': (_i, [_vp, _pp]),
+    'b200sift_set_blocking_sync': (_i, [_vp, _i]),
     'b200sift_last_kernel_ms': (_i, [_vp, C.POINTER(C.c_float)]),
     'b200sift_launch_count': (_i, [_vp, C.POINTER(C.c_longlong)]),
     'b200sift_sync': (_i, [_vp]),
@@ -159,6 +160,10 @@ class Context:
 
     def set_stream(self, cuda_stream_ptr):
         check(self.lib.b200sift_set_stream(self.handle, C.c_void_p(cuda_stream_ptr or 0)))
+
+    def set_blocking_sync(self, on):
+        """Sleep (True) or spin (False) while a synchronous call waits for the device."""
+        check(self.lib.b200sift_set_blocking_sync(self.handle, int(bool(on))))
 
     def stream_handle(self):
         """cudaStream_t (int) the context launches on."""

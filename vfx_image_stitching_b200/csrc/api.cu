@@ -4,6 +4,7 @@
 #include <math.h>
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
@@ -69,7 +70,7 @@ struct Timer {
     void stop()
     {
         cudaEventRecord(c->ev1, c->stream);
-        cudaEventSynchronize(c->ev1);
+        ctx_sync(c);
         cudaEventElapsedTime(&c->last_ms, c->ev0, c->ev1);
     }
 };
@@ -233,6 +234,10 @@ int b200sift_create(int device, b200sift_ctx **out)
     c->stream = c->own_stream;
     B200_CUDA(cudaEventCreate(&c->ev0));
     B200_CUDA(cudaEventCreate(&c->ev1));
+    B200_CUDA(cudaEventCreateWithFlags(&c->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
+    // default: spin unless the host has fewer than 8 hardware threads per visible GPU (one process per GPU
+    // with several contexts each would then have more waiting threads than cores)
+    c->blocking_sync = std::thread::hardware_concurrency() < 8u * (unsigned)n_dev;
     B200_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
     B200_CUDA(cudaStreamCreateWithFlags(&c->blur_side_stream, cudaStreamNonBlocking));
     B200_CUDA(cudaEventCreateWithFlags(&c->ev_seed, cudaEventDisableTiming));
@@ -248,7 +253,7 @@ void b200sift_destroy(b200sift_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    b200::ctx_sync(c);
     void *ptrs[] = {c->pyr.base, c->d_up, c->d_in, c->d_dog, c->d_cand, c->d_loc, c->d_raw, c->d_raw_desc,
                     c->d_sort_idx, c->d_keep, c->d_pos, c->d_class_idx, c->d_cub_tmp, c->d_kps, c->d_desc, c->d_counters,
                     c->d_mA, c->d_mB, c->d_mout, c->d_misc, c->d_pair, c->d_tc, c->d_tcsrc, c->d_seg, c->d_ptrs,
@@ -260,6 +265,7 @@ void b200sift_destroy(b200sift_ctx *c)
     if (c->h_pin) cudaFreeHost(c->h_pin);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    if (c->ev_sync) cudaEventDestroy(c->ev_sync);
     for (int o = 0; o < kMaxOctaves; ++o) cudaEventDestroy(c->ev_oct[o]);
     cudaEventDestroy(c->ev_side);
     cudaEventDestroy(c->ev_main);
@@ -277,6 +283,13 @@ int b200sift_set_stream(b200sift_ctx *c, void *s)
 {
     B200_ARG(c != nullptr);
     c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return 0;
+}
+
+int b200sift_set_blocking_sync(b200sift_ctx *c, int on)
+{
+    B200_ARG(c != nullptr);
+    c->blocking_sync = on != 0;
     return 0;
 }
 
@@ -304,7 +317,7 @@ int b200sift_launch_count(b200sift_ctx *c, long long *n)
 int b200sift_sync(b200sift_ctx *c)
 {
     B200_ARG(c != nullptr);
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     return 0;
 }
 
@@ -431,10 +444,10 @@ int b200sift_get_keypoints(b200sift_ctx *c, int image, b200sift_keypoint *kps, f
             B200_CUDA(cudaMemcpyAsync(tmp, c->d_desc + (size_t)off * 128, (size_t)n * 128, cudaMemcpyDeviceToHost,
                                       c->stream));
         }
-        B200_CUDA(cudaStreamSynchronize(c->stream));
+        B200_CUDA(b200::ctx_sync(c));
         for (size_t i = 0; i < (size_t)n * 128; ++i) desc_f32[i] = (float)tmp[i];
     }
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     return 0;
 }
 
@@ -457,7 +470,7 @@ int b200sift_get_all_keypoints(b200sift_ctx *c, b200sift_keypoint *kps, uint8_t 
                                   c->stream));
     if (desc_u8)
         B200_CUDA(cudaMemcpyAsync(desc_u8, c->d_desc, (size_t)n * 128, cudaMemcpyDeviceToHost, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     return 0;
 }
 
@@ -518,7 +531,7 @@ int b200sift_match(b200sift_ctx *c, const uint8_t *A, int nA, const uint8_t *B, 
     B200_CUDA(cudaMemcpyAsync(best_d2, d_b1, sizeof(int32_t) * nA, cudaMemcpyDeviceToHost, c->stream));
     if (second_d2)
         B200_CUDA(cudaMemcpyAsync(second_d2, d_b2, sizeof(int32_t) * nA, cudaMemcpyDeviceToHost, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     return 0;
 }
 
@@ -552,12 +565,12 @@ int b200sift_match_images(b200sift_ctx *c, int imgA, int imgB, int desc_thresh, 
     tm.stop();
     int32_t n = 0;
     B200_CUDA(cudaMemcpyAsync(&n, d_cnt, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     if (n > 0) {
         if (ia) B200_CUDA(cudaMemcpyAsync(ia, d_ia, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
         if (ib) B200_CUDA(cudaMemcpyAsync(ib, d_ib, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
         if (xyxy) B200_CUDA(cudaMemcpyAsync(xyxy, d_xy, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, c->stream));
-        B200_CUDA(cudaStreamSynchronize(c->stream));
+        B200_CUDA(b200::ctx_sync(c));
     }
     *n_matches = n;
     return 0;
@@ -592,7 +605,7 @@ int b200sift_match_pairs(b200sift_ctx *c, int n_pairs, const int32_t *pairs, int
     PairResult *res = static_cast<PairResult *>(c->h_pin);
     B200_CUDA(cudaMemcpyAsync(res, c->d_pair_res, sizeof(PairResult) * n_pairs, cudaMemcpyDeviceToHost, c->stream));
     tm.stop();
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     tl_mark(c->stream, "main  pair results on host");
     tl_report();
     c->pair_counts.assign(n_pairs, 0);
@@ -621,7 +634,7 @@ int b200sift_get_pair_matches(b200sift_ctx *c, int p, int32_t *ia, int32_t *ib, 
     if (ib) B200_CUDA(cudaMemcpyAsync(ib, c->d_pair_ib + mo, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
     if (xyxy)
         B200_CUDA(cudaMemcpyAsync(xyxy, c->d_pair_xy + 4 * mo, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     return 0;
 }
 
@@ -645,7 +658,7 @@ int b200sift_append_results(b200sift_ctx *c, const uint8_t *desc, const float *x
         // (x, y) are the first two floats of the 24-byte keypoint record
         B200_CUDA(cudaMemcpy2DAsync(c->d_kps + used, sizeof(b200sift_keypoint), xy, 2 * sizeof(float),
                                     2 * sizeof(float), n, kind, c->stream));
-        if (!on_device) B200_CUDA(cudaStreamSynchronize(c->stream));
+        if (!on_device) B200_CUDA(b200::ctx_sync(c));
     }
     *image_index = c->n_img_last;
     c->img_off.push_back(used + n);
@@ -738,7 +751,7 @@ static int grow_results(b200sift_ctx *c, int used, int need)
     B200_CUDA(cudaMemcpyAsync(nk, c->d_kps, sizeof(b200sift_keypoint) * (size_t)used, cudaMemcpyDeviceToDevice,
                               c->stream));
     B200_CUDA(cudaMemcpyAsync(nd, c->d_desc, (size_t)used * 128, cudaMemcpyDeviceToDevice, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     cudaFree(c->d_kps);
     cudaFree(c->d_desc);
     c->d_kps = nk;
@@ -790,7 +803,7 @@ int b200sift_unpack_exchange(b200sift_ctx *c, const void *gathered, int world, i
         c->h_pin_cap = need_pin * 2;
     }
     B200_CUDA(cudaMemcpy2DAsync(c->h_pin, kXRow, gathered, block, kXRow, world, cudaMemcpyDeviceToHost, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     memcpy(headers, c->h_pin, need_pin);
     if (src < 0) return 0;
     const int n = headers[(size_t)src * 34];
@@ -903,7 +916,7 @@ int b200sift_gaussian_blur(b200sift_ctx *c, const float *src, int h, int w, doub
     tm.stop();
     B200_CUDA(cudaMemcpy2DAsync(dst, (size_t)w * 4, d_dst, (size_t)pitch * 4, (size_t)w * 4, h,
                                 cudaMemcpyDeviceToHost, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     return 0;
 }
 
@@ -928,7 +941,7 @@ int b200sift_base_image(b200sift_ctx *c, const float *image, int h, int w, doubl
                            0, 0, 0, 0));
     B200_CUDA(cudaMemcpy2DAsync(out, (size_t)W * 4, d_dst, (size_t)pitch * 4, (size_t)W * 4, H,
                                 cudaMemcpyDeviceToHost, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     return 0;
 }
 
@@ -950,7 +963,7 @@ int b200sift_gaussian_pyramid(b200sift_ctx *c, const float *base, int h, int w, 
             B200_CUDA(cudaMemcpy2DAsync(dst, (size_t)p.w[o] * 4, p.layer(o, l), (size_t)p.pitch[o] * 4,
                                         (size_t)p.w[o] * 4, p.h[o], cudaMemcpyDeviceToHost, c->stream));
         }
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     return 0;
 }
 
@@ -975,7 +988,7 @@ int b200sift_dog_pyramid(b200sift_ctx *c, const float *const *layers, int h, int
             B200_CUDA(cudaMemcpy2DAsync(dst, (size_t)p.w[o] * 4, c->d_dog, (size_t)p.pitch[o] * 4,
                                         (size_t)p.w[o] * 4, p.h[o], cudaMemcpyDeviceToHost, c->stream));
         }
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     return 0;
 }
 
@@ -1004,7 +1017,7 @@ int b200sift_find_extrema(b200sift_ctx *c, const b200sift_params *params, const 
         B200_ARG(kps != nullptr);
         B200_CUDA(cudaMemcpyAsync(kps, c->d_kps, sizeof(b200sift_keypoint) * n_raw, cudaMemcpyDeviceToHost,
                                   c->stream));
-        B200_CUDA(cudaStreamSynchronize(c->stream));
+        B200_CUDA(b200::ctx_sync(c));
     }
     return 0;
 }
@@ -1029,7 +1042,7 @@ int b200sift_extrema_candidates(b200sift_ctx *c, const b200sift_params *params, 
     if (nc == 0) return 0;
     std::vector<Candidate> hc(nc);
     B200_CUDA(cudaMemcpyAsync(hc.data(), c->d_cand, sizeof(Candidate) * nc, cudaMemcpyDeviceToHost, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     // device order is arbitrary (atomic compaction); hand back the reference's scan order
     std::vector<uint64_t> key(nc);
     for (int i = 0; i < nc; ++i)
@@ -1067,7 +1080,7 @@ int b200sift_remove_duplicates(b200sift_ctx *c, b200sift_keypoint *kps, int n, i
     B200_CHECK(run_sort_gather(c, n, 1, 0, 1, 0, 0));
     const int m = c->img_off[1];
     B200_CUDA(cudaMemcpyAsync(kps, c->d_kps, sizeof(b200sift_keypoint) * m, cudaMemcpyDeviceToHost, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     *n_out = m;
     return 0;
 }
@@ -1103,7 +1116,7 @@ int b200sift_descriptors(b200sift_ctx *c, const b200sift_params *params, const b
     B200_CHECK(run_describe(c, P, c->d_raw, n, /*converted=*/1, d_out, 0));
     std::vector<uint8_t> u8((size_t)n * dlen);
     B200_CUDA(cudaMemcpyAsync(u8.data(), d_out, u8.size(), cudaMemcpyDeviceToHost, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     for (size_t i = 0; i < u8.size(); ++i) desc_f32[i] = (float)u8[i];
     return 0;
 }
@@ -1178,11 +1191,11 @@ int b200sift_ratio_match(b200sift_ctx *c, const uint8_t *A, int nA, const uint8_
     B200_CUDA(cudaMemcpyAsync(&n, d_cnt, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
     if (best_d2) B200_CUDA(cudaMemcpyAsync(best_d2, d_b1, sizeof(int32_t) * nA, cudaMemcpyDeviceToHost, c->stream));
     if (second_d2) B200_CUDA(cudaMemcpyAsync(second_d2, d_b2, sizeof(int32_t) * nA, cudaMemcpyDeviceToHost, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     if (n > 0) {
         if (ia) B200_CUDA(cudaMemcpyAsync(ia, d_ia, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
         if (ib) B200_CUDA(cudaMemcpyAsync(ib, d_ib, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
-        B200_CUDA(cudaStreamSynchronize(c->stream));
+        B200_CUDA(b200::ctx_sync(c));
     }
     *n_good = n;
     return 0;
@@ -1211,7 +1224,7 @@ int b200sift_cylindrical_projection(b200sift_ctx *c, const uint8_t *src, int h, 
     B200_CUDA(cudaMemcpyAsync(c->d_mA, src, bytes, cudaMemcpyHostToDevice, c->stream));
     B200_CHECK(launch_cyl(c, c->d_mA, h, w, ch, focal, c->d_mB));
     B200_CUDA(cudaMemcpyAsync(dst, c->d_mB, bytes, cudaMemcpyDeviceToHost, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     return 0;
 }
 

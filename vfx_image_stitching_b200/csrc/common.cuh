@@ -141,6 +141,10 @@ struct b200sift_ctx {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // host waits: spinning (lowest latency) or, when host cores are scarce (several ranks / contexts per
+    // core), sleeping on an event created with cudaEventBlockingSync
+    bool blocking_sync = false;
+    cudaEvent_t ev_sync = nullptr;
     // second stream: the extrema scan of octave o overlaps the blurs of octaves > o, and the keypoint
     // sort overlaps the descriptor kernel (dependencies by events, no host involvement)
     cudaStream_t side_stream = nullptr;
@@ -202,6 +206,14 @@ struct b200sift_ctx {
 };
 
 namespace b200 {
+
+// wait on the host until everything queued on the context's stream has run
+inline cudaError_t ctx_sync(b200sift_ctx *c)
+{
+    if (!c->blocking_sync || !c->ev_sync) return cudaStreamSynchronize(c->stream);
+    cudaError_t e = cudaEventRecord(c->ev_sync, c->stream);
+    return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_sync);
+}
 
 template <typename T>
 int ensure(T **p, size_t *cap, size_t need)

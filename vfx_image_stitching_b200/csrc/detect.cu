@@ -1114,7 +1114,7 @@ int run_detect(b200sift_ctx *c, const b200sift_params &p, int use_dog)
         B200_CUDA(cudaGetLastError());
         B200_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int32_t) * n_cnt, cudaMemcpyDeviceToHost,
                                   c->stream));
-        B200_CUDA(cudaStreamSynchronize(c->stream));
+        B200_CUDA(b200::ctx_sync(c));
         tl_mark(c->stream, "main  counters on host");
         const int nc = c->h_counters[CNT_CAND], nl = c->h_counters[CNT_LOC], nr = c->h_counters[CNT_RAW];
         if (nc <= c->cand_cap && nl <= c->loc_cap && nr <= c->raw_cap) return 0;
@@ -1197,7 +1197,7 @@ int run_sort_async(b200sift_ctx *c, int n_raw, int n_img, int scan_order, int de
     B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, c->d_keep, c->d_pos, n_raw, ss));
     if (tmp2 > tmp) tmp = tmp2;
     if (tmp > c->cub_tmp_cap) {
-        B200_CUDA(cudaStreamSynchronize(c->stream));
+        B200_CUDA(b200::ctx_sync(c));
         if (c->d_cub_tmp) cudaFree(c->d_cub_tmp);
         c->d_cub_tmp = nullptr;
         B200_CUDA(cudaMalloc(&c->d_cub_tmp, tmp + 1024));
@@ -1263,7 +1263,7 @@ int run_gather(b200sift_ctx *c, int n_raw, int n_img, int dedupe, int convert, i
     const int n_cnt = CNT_HDR + n_img * CNT_PER_IMG;
     B200_CUDA(cudaMemcpyAsync(c->h_counters, c->d_counters, sizeof(int32_t) * n_cnt, cudaMemcpyDeviceToHost,
                               c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     for (int i = 0; i < n_img; ++i) c->img_off[i + 1] = c->img_off[i] + c->h_counters[CNT_HDR + i * CNT_PER_IMG + 3];
     return 0;
 }
@@ -1355,7 +1355,7 @@ int launch_ransac(b200sift_ctx *c, const double *d_matches, int n, double thr, d
     B200_CUDA(cudaGetLastError());
     double res[3];
     B200_CUDA(cudaMemcpyAsync(res, d_out, sizeof(res), cudaMemcpyDeviceToHost, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     *best = (int32_t)res[0];
     move[0] = res[1];
     move[1] = res[2];
@@ -1403,7 +1403,7 @@ int run_localize_direct(b200sift_ctx *c, const b200sift_params &p, int use_dog, 
     B200_CUDA(cudaGetLastError());
     std::vector<Localized> hl(n);
     B200_CUDA(cudaMemcpyAsync(hl.data(), c->d_loc, sizeof(Localized) * n, cudaMemcpyDeviceToHost, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));   // also covers the copy out of `hc`
+    B200_CUDA(b200::ctx_sync(c));   // also covers the copy out of `hc`
     for (int i = 0; i < n; ++i) {
         const bool ok = hl[i].img_o_l != 0xFFFFFFFFu;
         b200sift_keypoint k;
@@ -1453,7 +1453,7 @@ int run_orient_direct(b200sift_ctx *c, const b200sift_params &p, const b200sift_
     B200_CUDA(cudaMemcpyAsync(h_counts, d_counts, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c->stream));
     B200_CUDA(cudaMemcpyAsync(hr.data(), c->d_raw, sizeof(RawKeypoint) * hr.size(), cudaMemcpyDeviceToHost,
                               c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     for (int i = 0; i < n; ++i)
         for (int k = 0; k < h_counts[i]; ++k) {
             const RawKeypoint &r = hr[(size_t)i * nb + k];

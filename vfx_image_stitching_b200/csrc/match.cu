@@ -273,7 +273,7 @@ static int scan_keep(b200sift_ctx *c, int n)
     size_t tmp = 0;
     B200_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->d_keep, c->d_pos, n, c->stream));
     if (tmp > c->cub_tmp_cap) {
-        B200_CUDA(cudaStreamSynchronize(c->stream));
+        B200_CUDA(b200::ctx_sync(c));
         if (c->d_cub_tmp) cudaFree(c->d_cub_tmp);
         c->d_cub_tmp = nullptr;
         B200_CUDA(cudaMalloc(&c->d_cub_tmp, tmp + 1024));

@@ -54,7 +54,7 @@ static int upload_taps(b200sift_ctx *c, int set, double sigma, int *radius)
     if (!c->d_taps) B200_CUDA(cudaMalloc((void **)&c->d_taps, sizeof(tc.taps)));
     // The host mirror of a set is rewritten below while an earlier asynchronous copy of the same set
     // could still be reading it: wait for the stream first (rare: only when a sigma changes).
-    if (tc.valid[set]) B200_CUDA(cudaStreamSynchronize(c->stream));
+    if (tc.valid[set]) B200_CUDA(b200::ctx_sync(c));
     memcpy(tc.taps[set], taps, sizeof(taps));
     // stream-ordered: later launches of this context see the new set, earlier ones the old
     B200_CUDA(cudaMemcpyAsync(c->d_taps + (size_t)set * (kMaxBlurRadius + 1), tc.taps[set], sizeof(taps),

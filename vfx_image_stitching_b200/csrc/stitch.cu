@@ -221,7 +221,7 @@ int b200sift_blend_two_images(b200sift_ctx *c, const uint8_t *imgA, int hA, int 
     c->launches += 3;
     B200_CUDA(cudaGetLastError());
     B200_CUDA(cudaMemcpyAsync(out, dO, nO, cudaMemcpyDeviceToHost, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     return 0;
 }
 
@@ -245,6 +245,6 @@ int b200sift_crop_bbox(b200sift_ctx *c, const uint8_t *img, int h, int w, int bl
     c->launches++;
     B200_CUDA(cudaGetLastError());
     B200_CUDA(cudaMemcpyAsync(box, c->d_mout, sizeof(init), cudaMemcpyDeviceToHost, c->stream));
-    B200_CUDA(cudaStreamSynchronize(c->stream));
+    B200_CUDA(b200::ctx_sync(c));
     return 0;
 }
