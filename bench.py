@@ -226,6 +226,7 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--depth', type=int, default=4, help='steps in flight per GPU (library contexts per rank)')
+    ap.add_argument('--sync-mode', type=int, default=-1, help='host wait of the library: 0 spin, 1 poll+yield, 2 sleep (-1: library default)')
     ap.add_argument('--no-extra', action='store_true', help='skip the frames (configs[3]) and matcher (configs[4]) legs')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
@@ -306,6 +307,9 @@ def main():
     DEPTH = args.depth      # image sets in flight per GPU (library contexts per rank)
     extra_ctx = [_capi.Context(local) for _ in range(DEPTH - 1)]
     all_ctx = [ctx] + extra_ctx
+    if args.sync_mode >= 0:
+        for c_ in all_ctx:
+            c_.set_sync_mode(args.sync_mode)
 
     def launches_now():
         return sum(c.launch_count() for c in all_ctx)

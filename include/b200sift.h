@@ -91,11 +91,12 @@ B200SIFT_API void b200sift_destroy(b200sift_ctx *ctx);
  * context's own stream).  Lets a torch caller order work on its stream. */
 B200SIFT_API int b200sift_set_stream(b200sift_ctx *ctx, void *cuda_stream);
 
-/* How the calling thread waits for the device inside the synchronous entry points: on != 0 sleeps on a
- * cudaEventBlockingSync event (frees the core; for hosts with fewer cores than waiting threads, e.g. eight
- * ranks with several contexts each), 0 spins (lowest latency).  Default: spin unless the host has fewer
- * than 8 hardware threads per visible GPU. */
-B200SIFT_API int b200sift_set_blocking_sync(b200sift_ctx *ctx, int on);
+/* How the calling thread waits for the device inside the synchronous entry points: 0 = spin (lowest
+ * latency), 1 = poll and sched_yield() between polls (for hosts with fewer cores than waiting threads,
+ * e.g. eight ranks with several contexts each on 32 cores), 2 = sleep on a cudaEventBlockingSync event
+ * (frees the core entirely; wake-ups cost tens of microseconds).  Default: 0, or 1 when the host has
+ * fewer than 8 hardware threads per visible GPU. */
+B200SIFT_API int b200sift_set_sync_mode(b200sift_ctx *ctx, int mode);
 
 /* The CUDA stream (cudaStream_t) the context currently launches on: its own, or the one given to
  * b200sift_set_stream.  Lets a host framework order its own streams against the library's work. */

@@ -45,7 +45,7 @@ PROTOTYPES = {
     'b200sift_destroy': (None, [_vp]),
     'b200sift_set_stream': (_i, [_vp, _vp]),
     'b200sift_get_stream': (_i, [_vp, _pp]),
-    'b200sift_set_blocking_sync': (_i, [_vp, _i]),
+    'b200sift_set_sync_mode': (_i, [_vp, _i]),
     'b200sift_last_kernel_ms': (_i, [_vp, C.POINTER(C.c_float)]),
     'b200sift_launch_count': (_i, [_vp, C.POINTER(C.c_longlong)]),
     'b200sift_sync': (_i, [_vp]),
@@ -161,9 +161,9 @@ class Context:
     def set_stream(self, cuda_stream_ptr):
         check(self.lib.b200sift_set_stream(self.handle, C.c_void_p(cuda_stream_ptr or 0)))
 
-    def set_blocking_sync(self, on):
-        """Sleep (True) or spin (False) while a synchronous call waits for the device."""
-        check(self.lib.b200sift_set_blocking_sync(self.handle, int(bool(on))))
+    def set_sync_mode(self, mode):
+        """0 spin, 1 poll + yield, 2 sleep while a synchronous call waits for the device."""
+        check(self.lib.b200sift_set_sync_mode(self.handle, int(mode)))
 
     def stream_handle(self):
         """cudaStream_t (int) the context launches on."""

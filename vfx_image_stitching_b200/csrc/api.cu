@@ -235,9 +235,9 @@ int b200sift_create(int device, b200sift_ctx **out)
     B200_CUDA(cudaEventCreate(&c->ev0));
     B200_CUDA(cudaEventCreate(&c->ev1));
     B200_CUDA(cudaEventCreateWithFlags(&c->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
-    // default: spin unless the host has fewer than 8 hardware threads per visible GPU (one process per GPU
-    // with several contexts each would then have more waiting threads than cores)
-    c->blocking_sync = std::thread::hardware_concurrency() < 8u * (unsigned)n_dev;
+    // default: spin; poll + yield when the host has fewer than 8 hardware threads per visible GPU (one
+    // process per GPU with several contexts each then has more waiting threads than cores)
+    c->sync_mode = std::thread::hardware_concurrency() < 8u * (unsigned)n_dev ? 1 : 0;
     B200_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
     B200_CUDA(cudaStreamCreateWithFlags(&c->blur_side_stream, cudaStreamNonBlocking));
     B200_CUDA(cudaEventCreateWithFlags(&c->ev_seed, cudaEventDisableTiming));
@@ -286,10 +286,10 @@ int b200sift_set_stream(b200sift_ctx *c, void *s)
     return 0;
 }
 
-int b200sift_set_blocking_sync(b200sift_ctx *c, int on)
+int b200sift_set_sync_mode(b200sift_ctx *c, int mode)
 {
-    B200_ARG(c != nullptr);
-    c->blocking_sync = on != 0;
+    B200_ARG(c != nullptr && mode >= 0 && mode <= 2);
+    c->sync_mode = mode;
     return 0;
 }
 

@@ -1,6 +1,7 @@
 // Shared declarations of the b200sift CUDA library (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -143,7 +144,7 @@ struct b200sift_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // host waits: spinning (lowest latency) or, when host cores are scarce (several ranks / contexts per
     // core), sleeping on an event created with cudaEventBlockingSync
-    bool blocking_sync = false;
+    int sync_mode = 0;   // 0 spin, 1 poll + sched_yield, 2 sleep
     cudaEvent_t ev_sync = nullptr;
     // second stream: the extrema scan of octave o overlaps the blurs of octaves > o, and the keypoint
     // sort overlaps the descriptor kernel (dependencies by events, no host involvement)
@@ -210,9 +211,16 @@ namespace b200 {
 // wait on the host until everything queued on the context's stream has run
 inline cudaError_t ctx_sync(b200sift_ctx *c)
 {
-    if (!c->blocking_sync || !c->ev_sync) return cudaStreamSynchronize(c->stream);
+    if (c->sync_mode == 0 || !c->ev_sync) return cudaStreamSynchronize(c->stream);   // spin
     cudaError_t e = cudaEventRecord(c->ev_sync, c->stream);
-    return e != cudaSuccess ? e : cudaEventSynchronize(c->ev_sync);
+    if (e != cudaSuccess) return e;
+    if (c->sync_mode == 2) return cudaEventSynchronize(c->ev_sync);                   // sleep (cudaEventBlockingSync)
+    // mode 1: poll, and give the core away between polls once the wait is not a short one
+    for (int spins = 0;; ++spins) {
+        e = cudaEventQuery(c->ev_sync);
+        if (e != cudaErrorNotReady) return e;
+        if (spins > 64) sched_yield();
+    }
 }
 
 template <typename T>

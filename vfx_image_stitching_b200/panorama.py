@@ -276,7 +276,7 @@ def _exchange_and_match(backend, ransac_thr, desc_thresh, dist, device, rank, wo
         st['out_h'].copy_(st['out_d'], non_blocking=True)
         ev = None
         if torch.device(device).type == 'cuda':
-            ev = torch.cuda.Event(blocking=True)      # the collecting thread sleeps instead of spinning
+            ev = torch.cuda.Event()
             ev.record()
         return {'st': st, 'event': ev, 'n': n, 'world': world, 'maxb': maxb, 'cap': st['cap']}
     rows = np.zeros((max(hi - lo, 0), 3), np.float64)
