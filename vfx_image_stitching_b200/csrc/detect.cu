@@ -232,6 +232,12 @@ extrema_rows_kernel(PyrView v, const __grid_constant__ ExGroup grp, int border, 
             if (l >= 1 && l <= NI) { dprev[l - 1] = dcur[l - 1]; dcur[l - 1] = d; }
         }
         if (y < ybeg + 1) continue;
+        // most rows of a warp have no pixel above the contrast pre-threshold (:122,148) in any of the
+        // NI layers: skip the 3x3x3 comparisons there (the running row maxima above are kept up)
+        bool any_big = false;
+#pragma unroll
+        for (int li = 0; li < NI; ++li) any_big |= fabsf(dprev[li]) > thresh;
+        if (!__any_sync(0xffffffffu, any_big && out_lane)) continue;
         float M[ND], m[ND];
 #pragma unroll
         for (int l = 0; l < ND; ++l) {
