@@ -208,8 +208,10 @@ def reference_arm(args, rank):
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': data,
         'config': {'workload': WORKLOAD,
-                   'note': 'the reference is pure Python (no compiled sources, oracle/_ref does not exist); this arm '
-                           'times the C restatement oracle/sift_oracle.c on all host threads'},
+                   'note': 'the reference is pure Python (no compiled sources, oracle/_ref does not exist) and is absent '
+                           'from the GPU box; this arm times the C restatement oracle/sift_oracle.c (pinned against the '
+                           'reference by tests/golden) on all host threads.  The Python reference itself: 0.005-0.008 '
+                           'Mpix/s (BASELINE.md, 8 cores)'},
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'match_desc_pairs_per_s': dps, 'gpu_launches': 0,
@@ -545,7 +547,10 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             v, ms_cpu, sample, threads, dps = cpu_run(imgs, 1, 1, budget_s=40.0)
             cpu = {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port', 'sample': sample,
-                   'match_desc_pairs_per_s': dps}
+                   'match_desc_pairs_per_s': dps,
+                   'python_reference': 'not timed in this run: the reference is pure Python and does not travel to the GPU '
+                                       'box (/root/reference is absent there); BASELINE.md holds its timings measured in '
+                                       'the build container: 0.005-0.008 Mpix/s and 3.5-3.9e5 descriptor pairs/s on 8 cores'}
         line = {
             'metric': METRIC, 'value': mpix_step / (ms_dev / 1e3), 'unit': UNIT, 'n_gpus': world,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms_dev, 'higher_is_better': True,
