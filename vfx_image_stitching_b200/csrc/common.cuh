@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <sched.h>
+#include <time.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -215,11 +216,18 @@ inline cudaError_t ctx_sync(b200sift_ctx *c)
     cudaError_t e = cudaEventRecord(c->ev_sync, c->stream);
     if (e != cudaSuccess) return e;
     if (c->sync_mode == 2) return cudaEventSynchronize(c->ev_sync);                   // sleep (cudaEventBlockingSync)
-    // mode 1: poll, and give the core away between polls once the wait is not a short one
+    // mode 1: poll; give the core away between polls once the wait is not a short one, and sleep in
+    // short naps once it is a long one (several waiting threads per core must not starve the threads
+    // that launch work)
     for (int spins = 0;; ++spins) {
         e = cudaEventQuery(c->ev_sync);
         if (e != cudaErrorNotReady) return e;
-        if (spins > 64) sched_yield();
+        if (spins > 256) {
+            struct timespec ts = {0, 20000};
+            nanosleep(&ts, nullptr);
+        } else if (spins > 64) {
+            sched_yield();
+        }
     }
 }
 
