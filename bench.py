@@ -264,7 +264,7 @@ def main():
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
     ctx = _capi.default_context(local)
-    stream = torch.cuda.Stream(dev)
+    stream = torch.cuda.Stream(dev, priority=-1)     # the library's side streams run at the lowest priority
     ctx.set_stream(stream.cuda_stream)
 
     base_imgs, data = load_workload()

@@ -230,7 +230,14 @@ int b200sift_create(int device, b200sift_ctx **out)
     b200sift_ctx *c = new b200sift_ctx();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    B200_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    // The context's own stream carries the critical path of a call (the blur chain that seeds the next
+    // octave, refine -> orient -> describe); the two side streams carry work that only has to be done by the
+    // time the main stream joins them (layers 4-5 of an octave, the extrema scan of finished octaves, the
+    // keypoint sort).  Highest priority for the former, lowest for the latter: queued CTAs of the seed chain
+    // are scheduled before the side work that would otherwise fill the SMs first.
+    int prio_least = 0, prio_greatest = 0;
+    B200_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    B200_CUDA(cudaStreamCreateWithPriority(&c->own_stream, cudaStreamNonBlocking, prio_greatest));
     c->stream = c->own_stream;
     B200_CUDA(cudaEventCreate(&c->ev0));
     B200_CUDA(cudaEventCreate(&c->ev1));
@@ -238,8 +245,8 @@ int b200sift_create(int device, b200sift_ctx **out)
     // default: spin; poll + yield when the host has fewer than 8 hardware threads per visible GPU (one
     // process per GPU with several contexts each then has more waiting threads than cores)
     c->sync_mode = std::thread::hardware_concurrency() < 8u * (unsigned)n_dev ? 1 : 0;
-    B200_CUDA(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
-    B200_CUDA(cudaStreamCreateWithFlags(&c->blur_side_stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaStreamCreateWithPriority(&c->side_stream, cudaStreamNonBlocking, prio_least));
+    B200_CUDA(cudaStreamCreateWithPriority(&c->blur_side_stream, cudaStreamNonBlocking, prio_least));
     B200_CUDA(cudaEventCreateWithFlags(&c->ev_seed, cudaEventDisableTiming));
     B200_CUDA(cudaEventCreateWithFlags(&c->ev_blur_side, cudaEventDisableTiming));
     for (int o = 0; o < kMaxOctaves; ++o) B200_CUDA(cudaEventCreateWithFlags(&c->ev_oct[o], cudaEventDisableTiming));
