@@ -543,6 +543,35 @@ def main():
                 'algorithmic_bytes_per_launch': 8 * nb * 2 * h * 2 * w, 'peak_source': peak_src,
                 'timing': 'each launch alone between CUDA events on the launch stream, 256 MiB L2 flush before it',
                 'per_sigma': detail, 'large_shape_8x6144x8192': large}
+        # ---- the dominant kernel of the step is describe_kernel (28 % of the device time): bound by
+        # instruction issue, not by HBM or the tensor pipe.  Its duration is measured here (CUDA events around
+        # the launch, one step at a time, L2 flushed); the warp-instruction count of the same launch comes
+        # from the committed ncu capture (profiles/r2_describe_ncu.txt: same inputs, deterministic).
+        t_desc, n_desc = 0.0, 0
+        for i in range(5):
+            flush.fill_(i)
+            torch.cuda.synchronize()
+            sift_impl.detect_and_describe_batch(resident_base, ctx=ctx, download=False)
+            ms = C.c_float()
+            nk = C.c_int32()
+            _capi.check(lib.b200sift_last_describe_ms(ctx.handle, C.byref(ms), C.byref(nk)))
+            t_desc += ms.value / 5
+            n_desc = nk.value
+        winst = None
+        pth = os.path.join(ROOT, 'profiles', 'r2_describe_ncu.txt')
+        if os.path.exists(pth):
+            import re
+            mm = re.search(r'smsp__inst_executed\.sum\s+([0-9.]+) inst', open(pth).read())
+            winst = float(mm.group(1)) if mm else None
+        sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+        issue_peak = sm_count * 4 * (clocks['sm_max_mhz'] if clocks and clocks.get('sm_max_mhz') else 1965.0) * 1e6
+        roof_desc = {'bound': 'issue', 'kernel': 'describe_kernel (4x4x8 descriptors, one warp per oriented keypoint)',
+                     'ms': t_desc, 'keypoints': n_desc, 'keypoints_per_s': n_desc / (t_desc * 1e-3) if t_desc else None,
+                     'warp_instructions': winst, 'warp_instructions_source': 'profiles/r2_describe_ncu.txt (ncu --set full)',
+                     'achieved': winst / (t_desc * 1e-3) / 1e9 if (winst and t_desc) else None,
+                     'peak': issue_peak / 1e9, 'unit': 'G warp-instructions/s',
+                     'frac': winst / (t_desc * 1e-3) / issue_peak if (winst and t_desc) else None,
+                     'peak_source': f'{sm_count} SMs x 4 schedulers x 1 warp instruction per cycle at the maximum SM clock'}
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             v, ms_cpu, sample, threads, dps = cpu_run(imgs, 1, 1, budget_s=40.0)
@@ -573,7 +602,7 @@ def main():
             'single_step': {'ms_per_step': ms_one, 'value': mpix_step / (ms_one / 1e3), 'unit': UNIT,
                             'gpu_launches': launches_one},
             'match_desc_pairs_per_s': desc_pairs / (ms_dev / 1e3), 'image_pairs_per_s': (n - 1) / (ms_dev / 1e3),
-            'roofline': roof, 'cpu_baseline': cpu, 'clocks': clocks,
+            'roofline': roof, 'roofline_describe': roof_desc, 'cpu_baseline': cpu, 'clocks': clocks,
         }
         if strong:
             line['strong_18_images'] = strong

@@ -104,6 +104,10 @@ B200SIFT_API int b200sift_get_stream(b200sift_ctx *ctx, void **cuda_stream);
 /* Device time in ms of the kernels of the last detect_describe / match call
  * (CUDA events on the context stream; host<->device copies excluded). */
 B200SIFT_API int b200sift_last_kernel_ms(b200sift_ctx *ctx, float *ms);
+/* Device time in ms of the descriptor kernel alone in the last detect_describe (CUDA events on the context
+ * stream around its launch) and the number of oriented keypoints it described: the dominant kernel of the
+ * step, reported by bench.py next to the blur's roofline line. */
+B200SIFT_API int b200sift_last_describe_ms(b200sift_ctx *ctx, float *ms, int32_t *n_keypoints);
 /* Number of kernel launches issued by this context since creation. */
 B200SIFT_API int b200sift_launch_count(b200sift_ctx *ctx, long long *n);
 

@@ -47,6 +47,7 @@ PROTOTYPES = {
     'b200sift_get_stream': (_i, [_vp, _pp]),
     'b200sift_set_sync_mode': (_i, [_vp, _i]),
     'b200sift_last_kernel_ms': (_i, [_vp, C.POINTER(C.c_float)]),
+    'b200sift_last_describe_ms': (_i, [_vp, C.POINTER(C.c_float), _ip]),
     'b200sift_launch_count': (_i, [_vp, C.POINTER(C.c_longlong)]),
     'b200sift_sync': (_i, [_vp]),
     'b200sift_detect_describe': (_i, [_vp, C.POINTER(Params), _i, _pp, _i, _i, _i, _i, _sz, _i, _ip]),

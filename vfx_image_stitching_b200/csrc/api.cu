@@ -241,6 +241,8 @@ int b200sift_create(int device, b200sift_ctx **out)
     c->stream = c->own_stream;
     B200_CUDA(cudaEventCreate(&c->ev0));
     B200_CUDA(cudaEventCreate(&c->ev1));
+    B200_CUDA(cudaEventCreate(&c->ev_desc0));
+    B200_CUDA(cudaEventCreate(&c->ev_desc1));
     B200_CUDA(cudaEventCreateWithFlags(&c->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
     // default: spin; poll + yield when the host has fewer than 8 hardware threads per visible GPU (one
     // process per GPU with several contexts each then has more waiting threads than cores)
@@ -272,6 +274,8 @@ void b200sift_destroy(b200sift_ctx *c)
     if (c->h_pin) cudaFreeHost(c->h_pin);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    cudaEventDestroy(c->ev_desc0);
+    cudaEventDestroy(c->ev_desc1);
     if (c->ev_sync) cudaEventDestroy(c->ev_sync);
     for (int o = 0; o < kMaxOctaves; ++o) cudaEventDestroy(c->ev_oct[o]);
     cudaEventDestroy(c->ev_side);
@@ -311,6 +315,19 @@ int b200sift_last_kernel_ms(b200sift_ctx *c, float *ms)
 {
     B200_ARG(c && ms);
     *ms = c->last_ms;
+    return 0;
+}
+
+int b200sift_last_describe_ms(b200sift_ctx *c, float *ms, int32_t *n_keypoints)
+{
+    B200_ARG(c && ms);
+    *ms = 0.f;
+    if (n_keypoints) *n_keypoints = 0;
+    if (!c->desc_timed || !c->have_results) return 0;
+    B200_CUDA(cudaSetDevice(c->device));
+    B200_CUDA(cudaEventSynchronize(c->ev_desc1));
+    B200_CUDA(cudaEventElapsedTime(ms, c->ev_desc0, c->ev_desc1));
+    if (n_keypoints) *n_keypoints = c->h_counters[CNT_RAW];
     return 0;
 }
 
@@ -407,7 +424,10 @@ int b200sift_detect_describe(b200sift_ctx *c, const b200sift_params *params, int
     fill_stats(c);
     const int n_raw = c->h_counters[CNT_RAW];
     B200_CHECK(run_sort_async(c, n_raw, n_images, 0, 1));         // side stream, overlaps the descriptors
+    B200_CUDA(cudaEventRecord(c->ev_desc0, c->stream));
     B200_CHECK(run_describe(c, P, c->d_raw, n_raw, 0, c->d_raw_desc, 1));
+    B200_CUDA(cudaEventRecord(c->ev_desc1, c->stream));
+    c->desc_timed = n_raw > 0;
     tl_mark(c->stream, "main  describe");
     tr.mark(c, "describe (|| sort)");
     B200_CHECK(run_gather(c, n_raw, n_images, 1, 1, 1));

@@ -143,6 +143,8 @@ struct b200sift_ctx {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_desc0 = nullptr, ev_desc1 = nullptr;   // around the descriptor kernel of the last detect_describe
+    bool desc_timed = false;
     // host waits: spinning (lowest latency) or, when host cores are scarce (several ranks / contexts per
     // core), sleeping on an event created with cudaEventBlockingSync
     int sync_mode = 0;   // 0 spin, 1 poll + sched_yield, 2 sleep
