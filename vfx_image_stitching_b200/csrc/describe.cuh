@@ -13,7 +13,7 @@
 //   * enumeration.  For a fixed window row the pixels inside the rotated 4x4 grid (:429-430) form
 //     an INTERVAL of x; a lane derives the interval of its row analytically (32 rows = one band).
 //     Intervals are cut into chunks of 8 pixels and a table of 16-bit entries (first x, row, pixel
-//     count of the chunk; 544 B of shared memory) is filled by the row owners; an iteration then
+//     count of the chunk; 480 B of shared memory) is filled by the row owners; an iteration then
 //     takes 4U consecutive chunks: lane = (chunk slot, pixel of the chunk), ONE 16-bit load gives it
 //     its row and x -- no search, no per-pixel test of the other half of the window, and lanes of a
 //     quarter warp read 8 adjacent pixels (one 32 B sector per gathered row);
@@ -39,9 +39,9 @@ constexpr int kDescHistFloats = 128 * 32;
 #define B200SIFT_DESC_U 3
 #endif
 constexpr int kDescU = B200SIFT_DESC_U;   // chunk slots per lane and iteration (independent dependency chains)
-constexpr int kDescTab = 544;             // chunk table of one band of rows (bytes, 16-bit entries)
-constexpr int kDescMaxRowLen = 128;       // rows of up to 64 px: bands of 32 rows (<= 256 chunks); up to 128 px: bands of
-                                          // 16 rows (<= 256 chunks); longer rows (huge keypoints of the quirk): plain path
+constexpr int kDescTab = 480;             // chunk table of one band of rows (bytes, 16-bit entries): 13 warps per SM fit
+constexpr int kDescMaxRowLen = 128;       // rows of up to 64 px: bands of 30 rows (<= 240 chunks); up to 128 px: bands of
+                                          // 15 rows (<= 240 chunks); longer rows (huge keypoints of the quirk): plain path
 constexpr size_t kDescSmemPerWarp = kDescHistFloats * sizeof(float) + kDescTab;
 
 // atan2(y, x) mod 2 pi in units of ORIENTATION BINS (2 pi = 8 bins; sift_impl.py:416-417 followed by
@@ -300,7 +300,7 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
         if (total_px > 0 && nx <= kDescMaxRowLen) {
             const int xmin = clo - ptx, xmax = chi - ptx;
             __syncwarp();
-            const int band_rows = nx <= 64 ? 32 : 16;   // <= 8 resp. 16 chunks per row: at most 256 chunks per band
+            const int band_rows = nx <= 64 ? 30 : 15;   // <= 8 resp. 16 chunks per row: at most 240 chunks per band
             for (int band0 = 0; band0 < ny; band0 += band_rows) {
                 // ---- this lane's row of the band: interval [a, a + cnt) of window offsets
                 const int r = band0 + lane;
@@ -343,7 +343,7 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
                     if (lane >= d) cend += t;
                 }
                 const int cstart = cend - nch;
-                const int total = __shfl_sync(0xffffffffu, cend, 31);   // <= 256 chunks
+                const int total = __shfl_sync(0xffffffffu, cend, 31);   // <= 240 chunks
                 // chunk entry: bits 0-7 first x offset + 128 (|x| <= half_w + 1 <= 65 on this path),
                 // bits 8-12 row of the band, bits 13-15 pixels in the chunk - 1
                 for (int k = 0; k < nch; ++k)
