@@ -331,3 +331,25 @@ def _match_sets_bucketed(ref, test, tol_px=0.5, tol_oct=0.05):
                     best, bd = j, key
         idx[i] = best
     return float((idx >= 0).mean()), idx
+
+
+def test_descriptors_large_and_clipped_windows(si, oracle, golden):
+    """The three enumeration paths of describe_kernel: rows of up to 64 px (bands of 30 rows), up to 128 px
+    (bands of 15 rows) and the plain path beyond (the huge keypoints the non-convergence quirk of
+    sift_impl.py:169-211 can emit), with windows clipped by the image border -- against the oracle."""
+    gray = golden('out')['gray'][1].astype(np.float32)
+    base = oracle.generate_base_image(gray, 1.6, 0.5)
+    pyr = oracle.generate_gaussian_images(base, oracle.compute_number_of_octaves(base.shape),
+                                          oracle.generate_gaussian_kernels(1.6, 3))
+    raw = oracle.find_scale_space_extrema(pyr, None, 3, 1.6, 5)
+    kps = oracle.convert_keypoints_to_input_image_size(oracle.remove_duplicate_keypoints(raw))
+    rng = np.random.default_rng(1)
+    sel = kps[rng.permutation(len(kps))[:240]].copy()
+    for k, f in enumerate((1.0, 2.2, 4.5, 9.0, 20.0, 60.0)):        # half widths ~20 .. > image diagonal
+        sel['size'][k::6] *= f
+    ref = oracle.generate_descriptors(sel, pyr)
+    got = si.generate_descriptors(si.array_to_keypoints(sel), pyr)
+    diff = np.abs(got - ref)
+    per = [float(np.mean(diff[k::6].sum(1) == 0)) for k in range(6)]
+    report(f'descriptors, window scale x1 / 2.2 / 4.5 / 9 / 20 / 60: identical rows {per} max|diff| {diff.max():.0f}')
+    assert diff.max() <= 1 and min(per) >= 0.9
