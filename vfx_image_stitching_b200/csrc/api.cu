@@ -341,6 +341,7 @@ int b200sift_launch_count(b200sift_ctx *c, long long *n)
 int b200sift_sync(b200sift_ctx *c)
 {
     B200_ARG(c != nullptr);
+    B200_CUDA(cudaSetDevice(c->device));   // the event of sync modes 1 / 2 is recorded on the context's device
     B200_CUDA(b200::ctx_sync(c));
     return 0;
 }

@@ -230,30 +230,33 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
             cls_end[k] = acc;
         }
     }
-    auto next_item = [&]() -> int {
+    // The queue runs TWO keypoints ahead so that the warp never waits for the chain atomic -> class
+    // table -> keypoint record before it can start on the current window: `take` only issues the
+    // atomic; its answer is mapped to a keypoint (`resolve`, lane 0) after the window loop, the record
+    // is loaded before the normalisation epilogue and turned into a window after it.
+    auto take = [&]() -> int {
         int t = 0;
-        if (lane == 0) {
-            t = atomicAdd(&counters[CNT_WORK_DESC], 1);
-            if (class_idx && t < n) {
-                int k = 0, start = 0;
-#pragma unroll
-                for (int q = 0; q < kDescClasses - 1; ++q)
-                    if (t >= cls_end[q]) { k = q + 1; start = cls_end[q]; }
-                t = t < cls_end[kDescClasses - 1] ? class_idx[(size_t)k * class_stride + (t - start)] : n;
-            }
-        }
-        return __shfl_sync(0xffffffffu, t, 0);
+        if (lane == 0) t = atomicAdd(&counters[CNT_WORK_DESC], 1);
+        return t;   // valid in lane 0
     };
-    int ki = next_item();
-    DescWin W;
-    if (ki < n) W = desc_window(v, dp, raw[ki], converted);
-    while (ki < n) {
-        const int ki_next = next_item();
-        DescWin Wn;
-        if (ki_next < n) {
-            Wn = desc_window(v, dp, raw[ki_next], converted);
-            desc_prefetch(Wn, lane);
+    auto resolve = [&](int t) -> int {   // queue position -> keypoint index (lane 0), n = none left
+        if (lane == 0 && class_idx && t < n) {
+            int k = 0, start = 0;
+#pragma unroll
+            for (int q = 0; q < kDescClasses - 1; ++q)
+                if (t >= cls_end[q]) { k = q + 1; start = cls_end[q]; }
+            t = t < cls_end[kDescClasses - 1] ? class_idx[(size_t)k * class_stride + (t - start)] : n;
         }
+        return t;
+    };
+    int ki = __shfl_sync(0xffffffffu, resolve(take()), 0);
+    int ki_next = __shfl_sync(0xffffffffu, resolve(take()), 0);
+    DescWin W, Wn;
+    if (ki < n) W = desc_window(v, dp, raw[ki], converted);
+    if (ki_next < n) Wn = desc_window(v, dp, raw[ki_next], converted);
+    while (ki < n) {
+        const int t_after = take();   // the keypoint after the next one
+        if (ki_next < n) desc_prefetch(Wn, lane);
         const bool ok = W.img != nullptr;
         const int rows = W.rows, cols = W.cols, pitch = W.pitch, ptx = W.ptx, pty = W.pty, half_w = W.half_w;
         const float *img = W.img;
@@ -299,6 +302,8 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
         };
         if (total_px > 0 && nx <= kDescMaxRowLen) {
             const int xmin = clo - ptx, xmax = chi - ptx;
+            const bool use_sin = fabsf(sin_f) > 1e-3f, use_cos = fabsf(cos_f) > 1e-3f;
+            const float inv_sin = use_sin ? 1.f / sin_f : 0.f, inv_cos = use_cos ? 1.f / cos_f : 0.f;
             __syncwarp();
             const int band_rows = nx <= 64 ? 30 : 15;   // <= 8 resp. 16 chunks per row: at most 240 chunks per band
             for (int band0 = 0; band0 < ny; band0 += band_rows) {
@@ -310,24 +315,27 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
                     float xl = (float)xmin, xh = (float)xmax;
                     bool none = false;
                     const float b1 = fy * cos_f, b2 = -(fy * sin_f);
-                    if (fabsf(sin_f) > 1e-6f) {
-                        const float t0 = (-lim - b1) / sin_f, t1 = (lim - b1) / sin_f;
+                    // a term whose x coefficient is below 1e-3 moves by < 0.13 over the row: it is left to
+                    // the exact predicate (and decides "no pixel at all" when it is off by more than 1);
+                    // above 1e-3 the analytic bounds are good to 0.01 px (cancellation 1e-5 / 1e-3)
+                    if (use_sin) {
+                        const float t0 = (-lim - b1) * inv_sin, t1 = (lim - b1) * inv_sin;
                         xl = fmaxf(xl, fminf(t0, t1));
                         xh = fminf(xh, fmaxf(t0, t1));
                     } else if (!(fabsf(b1) < lim + 1.f)) {
                         none = true;
                     }
-                    if (fabsf(cos_f) > 1e-6f) {
-                        const float t0 = (-lim - b2) / cos_f, t1 = (lim - b2) / cos_f;
+                    if (use_cos) {
+                        const float t0 = (-lim - b2) * inv_cos, t1 = (lim - b2) * inv_cos;
                         xl = fmaxf(xl, fminf(t0, t1));
                         xh = fminf(xh, fmaxf(t0, t1));
                     } else if (!(fabsf(b2) < lim + 1.f)) {
                         none = true;
                     }
                     int b = -1;
-                    if (!none && xl <= xh + 4.f) {
-                        a = max(xmin, (int)floorf(xl) - 2);
-                        b = min(xmax, (int)ceilf(xh) + 2);
+                    if (!none && xl <= xh + 2.f) {
+                        a = max(xmin, (int)ceilf(xl) - 1);    // one pixel of slack on each side, then shrink
+                        b = min(xmax, (int)floorf(xh) + 1);
                         while (a <= b && !keep_px(a, fy)) ++a;
                         while (b >= a && !keep_px(b, fy)) --b;
                     } else {
@@ -405,6 +413,7 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
             }
         }
         __syncwarp();
+        const int r_after = resolve(t_after);   // lane 0: class-table load goes out, awaited after the sum below
 
         // fixed-order sum of the 32 private histograms: lane <-> elements lane + 32 q, 16 B loads in a
         // rotated order (the eight lanes of a quarter warp read eight different bank groups)
@@ -423,6 +432,9 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
             vq[q] = s;
             ss += (double)(s * s);
         }
+        const int ki_after = __shfl_sync(0xffffffffu, r_after, 0);
+        RawKeypoint Ka;
+        if (ki_after < n) Ka = raw[ki_after];   // first used after the stores of this descriptor
 #pragma unroll
         for (int sft = 16; sft > 0; sft >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, sft);
         const float thr = sqrtf((float)ss) * dp.descriptor_max_value_f;
@@ -445,6 +457,8 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
         __syncwarp();
         ki = ki_next;
         W = Wn;
+        ki_next = ki_after;
+        if (ki_after < n) Wn = desc_window(v, dp, Ka, converted);
     }
 }
 

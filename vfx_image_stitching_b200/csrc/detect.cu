@@ -499,9 +499,15 @@ __device__ __forceinline__ float mod360f(float a)  // np.float32 % 360 for |a| <
 // conflict free); the lanes' histograms are then summed in a fixed order, so
 // the result is deterministic (no atomics).
 // ---------------------------------------------------------------------------
+// 2^-k as a float (0 <= k <= 126): dividing by 2^k and multiplying by this give the same float
+__device__ __forceinline__ float pow2_neg(int k) { return __int_as_float((127 - k) << 23); }
+
 constexpr int kOriWarps = 4;
 constexpr int kOriMaxBins = 36;
-__global__ void __launch_bounds__(kOriWarps * 32)
+#ifndef B200SIFT_ORI_MINB
+#define B200SIFT_ORI_MINB 5
+#endif
+__global__ void __launch_bounds__(kOriWarps * 32, B200SIFT_ORI_MINB)
 orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int loc_cap,
               RawKeypoint *__restrict__ raw, int raw_cap, int32_t *__restrict__ counters, int direct_n,
               int32_t *__restrict__ direct_counts, int32_t *__restrict__ class_idx)
@@ -510,30 +516,35 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
     // caller's keypoints and ONE Gaussian image, held by `v` as octave 0 / layer 0): the peaks of
     // keypoint i go to raw[i * ori_bins ...] in ascending bin order, their number to direct_counts[i].
     const bool direct = direct_n >= 0;
-    __shared__ double hist_s[kOriWarps][kOriMaxBins][32];
-    __shared__ double raw_s[kOriWarps][kOriMaxBins];
-    __shared__ double smooth_s[kOriWarps][kOriMaxBins];
+    __shared__ __align__(16) double hist_s[kOriWarps][kOriMaxBins][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nb = dp.ori_bins;  // <= 36
     const int n = direct ? direct_n : min(counters[CNT_LOC], loc_cap);
     const int warps_total = gridDim.x * kOriWarps;
     double(*hist)[32] = hist_s[wib];
+    // the summed and the smoothed histogram reuse the first rows of the private bins once those are summed
+    double *raw_h = &hist[0][0], *smooth_h = &hist[2][0];
+    static_assert(kOriMaxBins <= 36 && kOriMaxBins <= 64, "bins past 31 are summed in one round of four");
     (void)warps_total;
     // dynamic work queue: windows are (2r+1)^2 with r = 7..17.  The next item is fetched one keypoint
     // ahead and the 128 B lines of its window are requested into L2 while this one is evaluated (the
     // layer was last touched by the blur kernels and mostly left L2 since).
-    auto next_item = [&]() -> int {
+    // The queue runs TWO items ahead: `take` only issues the atomic (its value is broadcast after the
+    // pixel loop of the current keypoint, when it has long arrived), the Localized record of that item
+    // is loaded before the histogram epilogue and first used at the top of the next keypoint -- the
+    // warp never waits for an atomic followed by a dependent load before it can start its work.
+    auto take = [&]() -> int {
         int t = 0;
         if (lane == 0) t = atomicAdd(&counters[CNT_WORK_ORI], 1);
-        return __shfl_sync(0xffffffffu, t, 0);
+        return t;   // valid in lane 0
     };
     auto prefetch_window = [&](const Localized &P) {
         const int po = (P.img_o_l >> 8) & 255, pov = direct ? 0 : po;
         const int ph = v.h[pov], pw = v.w[pov], pp = v.pitch[pov];
         const float *pimg = v.layer(pov, direct ? 0 : (int)(P.img_o_l & 255), P.img_o_l >> 16);
-        const float pscale = (float)(dp.scale_factor * (double)P.size) / (float)(1 << (po + 1));
+        const float pscale = (float)(dp.scale_factor * (double)P.size) * pow2_neg(po + 1);
         const int prad = (int)fminf(rintf(dp.radius_factor_f * pscale), 64.f);
-        const int pcy = (int)rintf(P.y / (float)(1 << po)), pcx = (int)rintf(P.x / (float)(1 << po));
+        const int pcy = (int)rintf(P.y * pow2_neg(po)), pcx = (int)rintf(P.x * pow2_neg(po));
         const int y0 = max(pcy - prad - 1, 0), y1 = min(pcy + prad + 1, ph - 1);
         const int x0 = max(pcx - prad - 1, 0), x1 = min(pcx + prad + 1, pw - 1);
         if (y1 < y0 || x1 < x0) return;
@@ -543,66 +554,73 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
             for (uintptr_t a = a0; a <= a1; a += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
         }
     };
-    int li = next_item();
-    Localized L;
+    int li = __shfl_sync(0xffffffffu, take(), 0);
+    int li_next = __shfl_sync(0xffffffffu, take(), 0);
+    Localized L, Ln;
     if (li < n) L = loc[li];
+    if (li_next < n) Ln = loc[li_next];
     while (li < n) {
-        const int li_next = next_item();
-        Localized Ln;
-        if (li_next < n) {
-            Ln = loc[li_next];
-            prefetch_window(Ln);
-        }
+        const int t_after = take();   // item after the next one
+        if (li_next < n) prefetch_window(Ln);
         const int img = L.img_o_l >> 16, o = (L.img_o_l >> 8) & 255, layer = L.img_o_l & 255;
         const int ov = direct ? 0 : o;
         const int h = v.h[ov], w = v.w[ov], pitch = v.pitch[ov];
         const float *gimg = v.layer(ov, direct ? 0 : layer, img);
-        const float scale = (float)(dp.scale_factor * (double)L.size) / (float)(1 << (o + 1));
+        // x / 2^o (:250-251, :259-260) as the exact product x * 2^-o
+        const float scale = (float)(dp.scale_factor * (double)L.size) * pow2_neg(o + 1);
         const int radius = (int)fminf(rintf(dp.radius_factor_f * scale), 1048576.f);
         const float weight_fac = -0.5f / (scale * scale);
         const float weight_fac2 = weight_fac * 1.4426950408889634f;   // exp(w d) = 2^(w log2(e) d)
-        const int cy = (int)rintf(L.y / (float)(1 << o));
-        const int cx = (int)rintf(L.x / (float)(1 << o));
-        for (int b = 0; b < nb; ++b) hist[b][lane] = 0.0;
+        const int cy = (int)rintf(L.y * pow2_neg(o));
+        const int cx = (int)rintf(L.x * pow2_neg(o));
+        {   // zero the nb x 32 private bins (256 B per bin) with 16 B stores
+            float4 *h4 = reinterpret_cast<float4 *>(&hist[0][0]);
+            for (int i = lane; i < nb * 16; i += 32) h4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
         // the window clipped to the pixels the reference does not skip (:262-264)
         const int ylo = max(cy - radius, 1), yhi = min(cy + radius, h - 2);
         const int xlo = max(cx - radius, 1), xhi = min(cx + radius, w - 2);
         const int nx = xhi - xlo + 1, ny = yhi - ylo + 1;
         const int total = (nx > 0 && ny > 0) ? nx * ny : 0;
         int yy = lane / max(nx, 1), xx = lane - yy * max(nx, 1);
+        const int q32 = 32 / max(nx, 1), r32 = 32 - q32 * max(nx, 1);   // 32 pixels further = q32 rows and r32 columns
+        const float bin_scale = (float)nb * (1.f / 360.f);
         // Two pixels per lane and iteration (straight-line code: the two sqrt / atan2 / exp chains
-        // overlap), and the gather of iteration i+1 is issued before the arithmetic of iteration i so
-        // that its L2 latency is covered; the histogram updates stay in pixel order.
-        int ny_[2], nx_[2];      // pixel coordinates of the iteration in flight
-        bool nlive[2];
-        float ng[2][4];
-        auto issue = [&](int idx) {
+        // overlap); the histogram updates stay in pixel order.
+        struct Stage {           // one iteration in flight: pixel coordinates and the four neighbours
+            int y[2], x[2];
+            bool live[2];
+            float g[2][4];
+        };
+        auto issue = [&](Stage &S, int idx) {
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                nlive[u] = idx + 32 * u < total;
-                ny_[u] = nlive[u] ? ylo + yy : ylo;
-                nx_[u] = nlive[u] ? xlo + xx : xlo;
-                xx += 32;
-                while (xx >= nx) { xx -= nx; ++yy; }
-                const float *p = gimg + (size_t)ny_[u] * pitch + nx_[u];
-                ng[u][0] = __ldg(p + 1);
-                ng[u][1] = __ldg(p - 1);
-                ng[u][2] = __ldg(p - pitch);
-                ng[u][3] = __ldg(p + pitch);
+                S.live[u] = idx + 32 * u < total;
+                S.y[u] = S.live[u] ? ylo + yy : ylo;
+                S.x[u] = S.live[u] ? xlo + xx : xlo;
+                xx += r32;
+                yy += q32;
+                if (xx >= nx) { xx -= nx; ++yy; }
+                const float *p = gimg + (size_t)S.y[u] * pitch + S.x[u];
+                S.g[u][0] = __ldg(p + 1);
+                S.g[u][1] = __ldg(p - 1);
+                S.g[u][2] = __ldg(p - pitch);
+                S.g[u][3] = __ldg(p + pitch);
             }
         };
-        if (total > 0) issue(lane);
-        for (int idx = lane; idx < total; idx += 64) {
+        // evaluate the iteration held by S; its registers are refilled with iteration idx_next first
+        auto consume = [&](Stage &S, int idx_next) {
             int cyv[2], cxv[2];
             bool live[2];
             float g[2][4];
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                cyv[u] = ny_[u]; cxv[u] = nx_[u]; live[u] = nlive[u];
+                cyv[u] = S.y[u]; cxv[u] = S.x[u]; live[u] = S.live[u];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) g[u][k] = ng[u][k];
+                for (int k = 0; k < 4; ++k) g[u][k] = S.g[u][k];
             }
-            if (idx + 64 < total) issue(idx + 64);
+            if (idx_next < total) issue(S, idx_next);
             int bin[2];
             float val[2];
 #pragma unroll
@@ -613,7 +631,7 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
                 const float mag = fast_sqrt(__fmaf_rn(gx, gx, gy * gy));
                 const float ang = atan2_deg_fast(gy, gx);
                 const float wgt = fast_ex2(weight_fac2 * (float)(dx * dx + dy * dy));
-                int bi = (int)rintf(ang * (float)nb / 360.f);  // ang in [0, 360]: bi in [0, nb]
+                int bi = (int)rintf(ang * bin_scale);          // ang in [0, 360]: bi in [0, nb]
                 if (bi >= nb) bi -= nb;                         // == bi % nb (:279)
                 bin[u] = live[u] ? bi : -1;
                 val[u] = wgt * mag;
@@ -621,9 +639,23 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
 #pragma unroll
             for (int u = 0; u < 2; ++u)
                 if (bin[u] >= 0) hist[bin[u]][lane] += (double)val[u];
+        };
+        // TWO iterations in flight (stages A, B; the issue order is the pixel order): one iteration of
+        // arithmetic does not cover an L2 round trip
+        Stage A, B;
+        if (total > 0) issue(A, lane);
+        if (lane + 64 < total) issue(B, lane + 64);
+        for (int idx = lane; idx < total; idx += 128) {
+            consume(A, idx + 128);
+            if (idx + 64 < total) consume(B, idx + 192);
         }
+        const int li_after = __shfl_sync(0xffffffffu, t_after, 0);
+        Localized La;
+        if (li_after < n) La = loc[li_after];
         __syncwarp();
-        for (int b = lane; b < nb; b += 32) {
+        double r_main = 0.0;
+        if (lane < nb) {   // bins 0..31: one per lane
+            const int b = lane;
             double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;  // fixed order, 4 chains
 #pragma unroll
             for (int l = 0; l < 32; l += 4) {
@@ -632,15 +664,31 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
                 s2 += hist[b][(l + 2 + lane) & 31];
                 s3 += hist[b][(l + 3 + lane) & 31];
             }
-            raw_s[wib][b] = (s0 + s1) + (s2 + s3);
+            r_main = (s0 + s1) + (s2 + s3);
         }
+        double r_past = 0.0;
+        const int b_past = 32 + (lane >> 3);
+        if (nb > 32) {   // bins past 31 (four of the 36): eight lanes per bin, fixed tree
+            const int sub = lane & 7;
+            if (b_past < nb)
+                r_past = (hist[b_past][4 * sub] + hist[b_past][4 * sub + 1]) +
+                         (hist[b_past][4 * sub + 2] + hist[b_past][4 * sub + 3]);
+            r_past += __shfl_xor_sync(0xffffffffu, r_past, 1);
+            r_past += __shfl_xor_sync(0xffffffffu, r_past, 2);
+            r_past += __shfl_xor_sync(0xffffffffu, r_past, 4);
+        }
+        __syncwarp();   // every private bin has been read: its first rows now hold the sums
+        if (lane < nb) raw_h[lane] = r_main;
+        if (b_past < nb && (lane & 7) == 0) raw_h[b_past] = r_past;
         __syncwarp();
         double mx = -1.0;
         for (int b = lane; b < nb; b += 32) {
-            const double *r = raw_s[wib];
-            const int m1 = (b + nb - 1) % nb, m2 = (b + nb - 2) % nb, p1 = (b + 1) % nb, p2 = (b + 2) % nb;
+            const double *r = raw_h;
+            // circular neighbours (:282-283); nb >= 4, so one conditional wrap each
+            const int m1 = b >= 1 ? b - 1 : b - 1 + nb, m2 = b >= 2 ? b - 2 : b - 2 + nb;
+            const int p1 = b + 1 < nb ? b + 1 : b + 1 - nb, p2 = b + 2 < nb ? b + 2 : b + 2 - nb;
             const double s = (6 * r[b] + 4 * (r[m1] + r[p1]) + r[m2] + r[p2]) / 16.;
-            smooth_s[wib][b] = s;
+            smooth_h[b] = s;
             mx = fmax(mx, s);
         }
 #pragma unroll
@@ -653,31 +701,31 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
             bool peak = false;
             double sl = 0, sr = 0, sc = 0;
             if (b < nb) {
-                const double *s = smooth_s[wib];
-                sl = s[(b + nb - 1) % nb];
-                sr = s[(b + 1) % nb];
+                const double *s = smooth_h;
+                sl = s[b >= 1 ? b - 1 : nb - 1];
+                sr = s[b + 1 < nb ? b + 1 : 0];
                 sc = s[b];
                 peak = (sc > sl) && (sc > sr) && (sc >= dp.peak_ratio * mx);
             }
             const unsigned m = __ballot_sync(0xffffffffu, peak);
             if (m) {
-                int base = 0;
+                // work class of the descriptor kernel: by window half-width (sift_impl.py:386-388)
+                const float hw = (float)dp.scale_multiplier_half * L.size * pow2_neg(o);   // hist_width (:386) in octave pixels
+                const float half_w = hw * 3.5355339f;
+                const int cls = half_w >= 40.f ? 0 : half_w >= 32.f ? 1 : half_w >= 26.f ? 2 : half_w >= 21.f ? 3 : 4;
+                int base = 0, cb = 0;
                 if (direct) {
                     base = li * nb + emitted;
                 } else {
-                    if (lane == __ffs(m) - 1) {
+                    if (lane == __ffs(m) - 1) {   // both slot atomics go out before either answer is awaited
                         base = atomicAdd(&counters[CNT_RAW], __popc(m));
+                        if (class_idx) cb = atomicAdd(&counters[CNT_CLASS + cls], __popc(m));
                         atomicAdd(&counters[CNT_HDR + img * CNT_PER_IMG + 2], __popc(m));
                     }
                     base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-                }
-                if (class_idx) {   // work class of the descriptor kernel: by window half-width (sift_impl.py:386-388)
-                    const float hw = (float)dp.scale_multiplier_half * L.size / (float)(1 << o);   // hist_width (:386) in octave pixels
-                    const float half_w = hw * 3.5355339f;
-                    const int cls = half_w >= 40.f ? 0 : half_w >= 32.f ? 1 : half_w >= 26.f ? 2 : half_w >= 21.f ? 3 : 4;
-                    int cb = 0;
-                    if (lane == __ffs(m) - 1) cb = atomicAdd(&counters[CNT_CLASS + cls], __popc(m));
                     cb = __shfl_sync(0xffffffffu, cb, __ffs(m) - 1);
+                }
+                if (class_idx) {
                     if (peak) {
                         const int slot = base + __popc(m & ((1u << lane) - 1u));
                         if (slot < raw_cap) class_idx[(size_t)cls * raw_cap + cb + __popc(m & ((1u << lane) - 1u))] = slot;
@@ -686,8 +734,9 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
                 if (peak) {
                     const int slot = base + __popc(m & ((1u << lane) - 1u));
                     double t = (double)b + 0.5 * (sl - sr) / (sl - 2 * sc + sr);
-                    double interp = fmod(t, (double)nb);
-                    if (interp != 0.0) { if (interp < 0) interp += (double)nb; } else interp = 0.0;
+                    // t % nb (:288): a strict peak has |t - b| <= 0.5, so -0.5 <= t < nb and the
+                    // remainder is t itself or, for t < 0, t + nb
+                    double interp = t < 0.0 ? t + (double)nb : t;
                     double angle = 360. - interp * 360. / (double)nb;
                     if (fabs(angle - 360.) < 1e-7) angle = 0;
                     if (slot < raw_cap) {
@@ -707,6 +756,8 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
         __syncwarp();
         li = li_next;
         L = Ln;
+        li_next = li_after;
+        Ln = La;
     }
 }
 
@@ -957,6 +1008,7 @@ image_offsets_kernel(const int *__restrict__ img_kept, int n_img, int *__restric
 }
 
 static int g_desc_occ = 1;  // resident describe CTAs per SM (kernel + sm_100 property; set under the init lock)
+static int g_ori_occ = 5;   // resident orient CTAs per SM, same
 
 // Function attributes are per DEVICE: called once for every device a context is created on
 // (b200sift_create, under the init lock), never from a launch path.
@@ -968,6 +1020,9 @@ int detect_init_device()
     int occ = 0;
     B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, describe_kernel, kDescWarps * 32, smem));
     g_desc_occ = occ < 1 ? 1 : occ;
+    B200_CUDA(cudaFuncSetAttribute(orient_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, orient_kernel, kOriWarps * 32, 0));
+    g_ori_occ = occ < 1 ? 1 : occ;
     B200_CUDA(cudaFuncSetAttribute(sort_image_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kSortMaxPerImage * kSortBytesPerSlot));
     B200_CUDA(cudaFuncSetAttribute(describe_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1111,7 +1166,7 @@ int run_detect(b200sift_ctx *c, const b200sift_params &p, int use_dog)
                                                                     c->loc_cap, c->d_counters, -1, 0);
             c->launches++;
             tl_mark(c->stream, "main  refine");
-            orient_kernel<<<c->sm_count * 5, kOriWarps * 32, 0, c->stream>>>(v, dp, c->d_loc, c->loc_cap, c->d_raw,
+            orient_kernel<<<c->sm_count * g_ori_occ, kOriWarps * 32, 0, c->stream>>>(v, dp, c->d_loc, c->loc_cap, c->d_raw,
                                                                              c->raw_cap, c->d_counters, -1, nullptr,
                                                                              c->d_class_idx);
             c->launches++;
