@@ -70,7 +70,7 @@ __device__ __forceinline__ float atan2_bins_fast(float y, float x)
 }
 
 struct DescGeom {
-    float cos_f, sin_f, inv_hw, angle_bins;
+    float cos_q, sin_q, angle_bins;   // cos, sin of the rotation divided by hist_width; angle in bins
 };
 
 // floor(x) for |x| < 2^22 without the conversion pipe: round-to-nearest of x - 0.5 through the
@@ -81,6 +81,14 @@ constexpr float kMagic = 12582912.f;   // 1.5 * 2^23
 __device__ __forceinline__ int floor_magic(float xm, float &fl)
 {
     const float t = xm + kMagic;
+    fl = t - kMagic;
+    return __float_as_int(t) - 0x4B400000;
+}
+
+// floor(x + 1.5) given x: the same with the + 1 folded into the magic constant (2^23 * 1.5 + 1 is exact)
+__device__ __forceinline__ int floor_magic1(float x, float &fl)
+{
+    const float t = x + (kMagic + 1.f);
     fl = t - kMagic;
     return __float_as_int(t) - 0x4B400000;
 }
@@ -99,13 +107,14 @@ __device__ __forceinline__ void desc_eval(float *__restrict__ hl, const float (&
     bool p[U][4];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-        const float r_rot = __fmaf_rn(fx[u], G.sin_f, fy[u] * G.cos_f);      // :421-422
-        const float c_rot = __fmaf_rn(fx[u], G.cos_f, -(fy[u] * G.sin_f));
-        const float qr = r_rot * G.inv_hw, qc = c_rot * G.inv_hw;
+        // (x sin + y cos) / hist_width and (x cos - y sin) / hist_width (:421-426), the division folded
+        // into the coefficients
+        const float qr = __fmaf_rn(fx[u], G.sin_q, fy[u] * G.cos_q);
+        const float qc = __fmaf_rn(fx[u], G.cos_q, -(fy[u] * G.sin_q));
         // r_bin = qr + 1.5 (:425); -1 < r_bin < 4 (:429-430)  <=>  |qr| < 2.5
         const bool in = live[u] && fabsf(qr) < 2.5f && fabsf(qc) < 2.5f;
         float r0f, c0f, o0f;
-        const int r0 = floor_magic(qr + 1.f, r0f), c0 = floor_magic(qc + 1.f, c0f);
+        const int r0 = floor_magic1(qr, r0f), c0 = floor_magic1(qc, c0f);   // floor(q + 1.5)
         const float rf = (qr + 1.5f) - r0f, cf = (qc + 1.5f) - c0f;
         const float gx = g[u][0] - g[u][1];
         const float gy = g[u][2] - g[u][3];
@@ -245,7 +254,8 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
 #pragma unroll
             for (int q = 0; q < kDescClasses - 1; ++q)
                 if (t >= cls_end[q]) { k = q + 1; start = cls_end[q]; }
-            t = t < cls_end[kDescClasses - 1] ? class_idx[(size_t)k * class_stride + (t - start)] : n;
+            // (a class can only outgrow its stride when the keypoint list overflowed; the stage is redone then)
+            t = (t < cls_end[kDescClasses - 1] && t - start < class_stride) ? class_idx[(size_t)k * class_stride + (t - start)] : n;
         }
         return t;
     };
@@ -264,11 +274,10 @@ describe_kernel(PyrView v, DetectParams dp, const RawKeypoint *__restrict__ raw,
         const double angle = 360. - (double)W.angle;
         const double rad = angle * (3.14159265358979323846 / 180.0);
         DescGeom G;
-        G.cos_f = (float)cos(rad);
-        G.sin_f = (float)sin(rad);
-        G.inv_hw = 1.f / hist_width;
+        const float cos_f = (float)cos(rad), sin_f = (float)sin(rad);
+        G.cos_q = cos_f / hist_width;
+        G.sin_q = sin_f / hist_width;
         G.angle_bins = (float)angle * (float)(8 / 360.);
-        const float cos_f = G.cos_f, sin_f = G.sin_f;
         const float lim = 2.5f * hist_width * 1.0001f + 1e-3f;  // float32 pre-filter of the enumeration, exact test per pixel
 
         {
