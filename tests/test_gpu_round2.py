@@ -353,3 +353,27 @@ def test_descriptors_large_and_clipped_windows(si, oracle, golden):
     per = [float(np.mean(diff[k::6].sum(1) == 0)) for k in range(6)]
     report(f'descriptors, window scale x1 / 2.2 / 4.5 / 9 / 20 / 60: identical rows {per} max|diff| {diff.max():.0f}')
     assert diff.max() <= 1 and min(per) >= 0.9
+
+
+def test_descriptors_near_axis_aligned_angles(si, oracle, golden):
+    """Row intervals of describe_kernel when sin or cos of the window rotation is tiny: below 1e-3 the term is
+    left to the exact per-pixel predicate, above it the analytic bound is used -- angles on both sides of the
+    switch around every multiple of 90 degrees, small and large windows, against the oracle."""
+    gray = golden('out')['gray'][1].astype(np.float32)
+    base = oracle.generate_base_image(gray, 1.6, 0.5)
+    pyr = oracle.generate_gaussian_images(base, oracle.compute_number_of_octaves(base.shape),
+                                          oracle.generate_gaussian_kernels(1.6, 3))
+    raw = oracle.find_scale_space_extrema(pyr, None, 3, 1.6, 5)
+    kps = oracle.convert_keypoints_to_input_image_size(oracle.remove_duplicate_keypoints(raw))
+    offs = np.array([0.0, 1e-5, 3e-4, 0.03, 0.056, 0.058, 0.07, 0.5], np.float64)     # 1e-3 rad = 0.0573 deg
+    angles = np.concatenate([(a + s * offs) % 360.0 for a in (0.0, 90.0, 180.0, 270.0) for s in (1, -1)])
+    rng = np.random.default_rng(5)
+    sel = kps[rng.permutation(len(kps))[:len(angles) * 3]].copy()
+    sel['angle'] = np.tile(angles, 3).astype(np.float32)
+    sel['size'][len(angles):2 * len(angles)] *= 2.5
+    sel['size'][2 * len(angles):] *= 5.0
+    ref = oracle.generate_descriptors(sel, pyr)
+    got = si.generate_descriptors(si.array_to_keypoints(sel), pyr)
+    diff = np.abs(got - ref)
+    report(f'descriptors at near-axis angles: identical rows {np.mean(diff.sum(1) == 0):.4f} max|diff| {diff.max():.0f}')
+    assert diff.max() <= 1 and np.mean(diff.sum(1) == 0) >= 0.97
