@@ -25,7 +25,10 @@
 //     to the oracle on the same pyramid, RMS relative L2 < 1e-3 end to end);
 //   * atan2 in degrees as one branch-free minimax polynomial (8 terms, <= 7e-6 deg, below the 3e-5
 //     deg float32 spacing of an angle near 360), MUFU approximations for sqrt / exp2 / reciprocal;
-//   * every histogram update is one FFMA between a shared-memory load and store.
+//   * every histogram update is one FFMA between a shared-memory load and store;
+//   * per keypoint: the work queue runs two keypoints ahead (the atomic, the class-table entry and the keypoint
+//     record are fetched behind the previous windows' arithmetic), the row intervals of a band come from two
+//     reciprocals per keypoint and start one pixel wide of the analytic bound.
 // Each lane adds its shares to a lane-private float32 4x4x8 histogram in shared memory
 // ([bin][lane]: conflict free, no atomics); only the inner 4x4 cells of the reference's 6x6 tensor
 // are ever read (:509), so shares of the border ring are dropped.  The 32 private histograms are
