@@ -504,10 +504,8 @@ __device__ __forceinline__ float pow2_neg(int k) { return __int_as_float((127 - 
 
 constexpr int kOriWarps = 4;
 constexpr int kOriMaxBins = 36;
-#ifndef B200SIFT_ORI_MINB
-#define B200SIFT_ORI_MINB 5
-#endif
-__global__ void __launch_bounds__(kOriWarps * 32, B200SIFT_ORI_MINB)
+// five CTAs per SM (36.9 KB of private bins each, 94 registers); a sixth (80 registers) measured slower
+__global__ void __launch_bounds__(kOriWarps * 32, 5)
 orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int loc_cap,
               RawKeypoint *__restrict__ raw, int raw_cap, int32_t *__restrict__ counters, int direct_n,
               int32_t *__restrict__ direct_counts, int32_t *__restrict__ class_idx)
@@ -520,16 +518,14 @@ orient_kernel(PyrView v, DetectParams dp, const Localized *__restrict__ loc, int
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int nb = dp.ori_bins;  // <= 36
     const int n = direct ? direct_n : min(counters[CNT_LOC], loc_cap);
-    const int warps_total = gridDim.x * kOriWarps;
     double(*hist)[32] = hist_s[wib];
     // the summed and the smoothed histogram reuse the first rows of the private bins once those are summed
     double *raw_h = &hist[0][0], *smooth_h = &hist[2][0];
-    static_assert(kOriMaxBins <= 36 && kOriMaxBins <= 64, "bins past 31 are summed in one round of four");
-    (void)warps_total;
-    // dynamic work queue: windows are (2r+1)^2 with r = 7..17.  The next item is fetched one keypoint
-    // ahead and the 128 B lines of its window are requested into L2 while this one is evaluated (the
-    // layer was last touched by the blur kernels and mostly left L2 since).
-    // The queue runs TWO items ahead: `take` only issues the atomic (its value is broadcast after the
+    static_assert(kOriMaxBins <= 36, "bins past 31 are summed in one round of four");
+    // dynamic work queue: windows are (2r+1)^2 with r = 7..17.  The 128 B lines of the NEXT item's window
+    // are requested into L2 while this one is evaluated (the layer was last touched by the blur kernels
+    // and mostly left L2 since).
+    // The queue itself runs TWO items ahead: `take` only issues the atomic (its value is broadcast after the
     // pixel loop of the current keypoint, when it has long arrived), the Localized record of that item
     // is loaded before the histogram epilogue and first used at the top of the next keypoint -- the
     // warp never waits for an atomic followed by a dependent load before it can start its work.
